@@ -1,0 +1,340 @@
+/*
+ * fs_oracle.c -- CPU restatement of futspace's render hot path (TEST INFRASTRUCTURE ONLY).
+ * See fs_oracle.h for the parity status ("parity unpinned" for the matte colour maths).
+ *
+ * Build: gcc -std=c11 -O2 -ffp-contract=off -fno-fast-math -fopenmp (oracle/Makefile).
+ * -ffp-contract=off matters: every f32 product and sum below is rounded separately, which is
+ * the float order north_star defines as "the reference's" (nvcc side: -fmad=false).
+ *
+ * All file:line citations are into /root/reference.
+ */
+#include "fs_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * i32.f32 / u32.f32 on values C leaves undefined (SURVEY.md fact 8, 8c last row).
+ * ---------------------------------------------------------------------------------------- */
+static inline int32_t f2i(float x, int mode) {
+  if (mode == FSO_F2I_SATURATE) { /* PTX cvt.rzi.s32.f32: what futhark opencl/cuda emit on NVIDIA */
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return INT32_MAX;
+    if (x <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)x;
+  }
+  if (mode == FSO_F2I_X86) { /* cvttss2si: "integer indefinite" for every invalid input */
+    if (x != x || x >= 2147483648.0f || x < -2147483648.0f) return INT32_MIN;
+    return (int32_t)x;
+  }
+  /* FSO_F2I_MODERN: futhark >= 0.19 C runtime: isnan||isinf -> 0, else a plain C cast */
+  if (x != x || isinf(x)) return 0;
+  if (x >= 2147483648.0f || x < -2147483648.0f) return INT32_MIN;
+  return (int32_t)x;
+}
+
+/* u32.f32 of a value already clamped to [0,255] or NaN (NaN -> 0 on every backend we model). */
+static inline uint32_t f2u_channel(float x) {
+  if (x != x) return 0u;
+  return (uint32_t)x;
+}
+
+/* Futhark's integer `%` rounds toward negative infinity: result in [0, n) for n > 0. */
+static inline int32_t floored_mod(int32_t a, int32_t n) {
+  int32_t m = a % n;
+  return m < 0 ? m + n : m;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * matte 0.1.2 `argb` (restated from the published algorithm; NOT in /root/reference).
+ * Call sites that define how it is used: fut/render_functions.fut:101-103 (mix),
+ * fut/interactive.fut:163 (scale).
+ * ---------------------------------------------------------------------------------------- */
+static inline void to_rgba(uint32_t c, float *r, float *g, float *b, float *a) {
+  *r = (float)((c >> 16) & 0xFFu) / 255.0f;
+  *g = (float)((c >> 8) & 0xFFu) / 255.0f;
+  *b = (float)(c & 0xFFu) / 255.0f;
+  *a = (float)((c >> 24) & 0xFFu) / 255.0f;
+}
+
+static inline float clamp_channel(float x) { /* NaN falls through both comparisons */
+  return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x);
+}
+
+static inline uint32_t from_rgba(float r, float g, float b, float a) {
+  return (f2u_channel(clamp_channel(a) * 255.0f) << 24) | (f2u_channel(clamp_channel(r) * 255.0f) << 16) |
+         (f2u_channel(clamp_channel(g) * 255.0f) << 8) | f2u_channel(clamp_channel(b) * 255.0f);
+}
+
+uint32_t fso_mix(float m1, uint32_t c1, float m2, uint32_t c2) {
+  float r1, g1, b1, a1, r2, g2, b2, a2;
+  to_rgba(c1, &r1, &g1, &b1, &a1);
+  to_rgba(c2, &r2, &g2, &b2, &a2);
+  float m12 = m1 + m2;
+  float m1n = m1 / m12;
+  float m2n = m2 / m12;
+  float r1s = r1 * r1, r2s = r2 * r2;
+  float g1s = g1 * g1, g2s = g2 * g2;
+  float b1s = b1 * b1, b2s = b2 * b2;
+  float t, u;
+  t = m1n * r1s; u = m2n * r2s; float r = sqrtf(t + u);
+  t = m1n * g1s; u = m2n * g2s; float g = sqrtf(t + u);
+  t = m1n * b1s; u = m2n * b2s; float b = sqrtf(t + u);
+  t = m1 * a1;   u = m2 * a2;   float a = (t + u) / m12;
+  return from_rgba(r, g, b, a);
+}
+
+uint32_t fso_scale(uint32_t c, float s) {
+  float r, g, b, a;
+  to_rgba(c, &r, &g, &b, &a);
+  return from_rgba(r * s, g * s, b * s, a * s);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Samplers.  fut/render_functions.fut
+ * ---------------------------------------------------------------------------------------- */
+/* :63-64  heights[(i32.f32 y)%h, (i32.f32 x)%w]  -- truncation toward zero, then floored mod */
+float fso_height_nearest(const int32_t *hm, int q, int r, float x, float y, int m) {
+  int32_t iy = floored_mod(f2i(y, m), q), ix = floored_mod(f2i(x, m), r);
+  return (float)hm[(size_t)iy * r + ix];
+}
+/* :91-92 */
+uint32_t fso_color_nearest(const uint32_t *cm, int q, int r, float x, float y, int m) {
+  int32_t iy = floored_mod(f2i(y, m), q), ix = floored_mod(f2i(x, m), r);
+  return cm[(size_t)iy * r + ix];
+}
+/* :67-77 */
+float fso_height_bilinear(const int32_t *hm, int q, int r, float x, float y, int m) {
+  float fx = floorf(x), cx = ceilf(x), fy = floorf(y), cy = ceilf(y);
+  int32_t x0 = floored_mod(f2i(fx, m), r), x1 = floored_mod(f2i(cx, m), r);
+  int32_t y0 = floored_mod(f2i(fy, m), q), y1 = floored_mod(f2i(cy, m), q);
+  float wx0 = cx - x, wx1 = x - fx, wy0 = cy - y, wy1 = y - fy;
+  float a, b;
+  a = wx0 * (float)hm[(size_t)y0 * r + x0];
+  b = wx1 * (float)hm[(size_t)y0 * r + x1];
+  float xi1 = a + b;
+  a = wx0 * (float)hm[(size_t)y1 * r + x0];
+  b = wx1 * (float)hm[(size_t)y1 * r + x1];
+  float xi2 = a + b;
+  a = wy0 * xi1;
+  b = wy1 * xi2;
+  return a + b;
+}
+/* :95-105 */
+uint32_t fso_color_bilinear(const uint32_t *cm, int q, int r, float x, float y, int m) {
+  float fx = floorf(x), cx = ceilf(x), fy = floorf(y), cy = ceilf(y);
+  int32_t x0 = floored_mod(f2i(fx, m), r), x1 = floored_mod(f2i(cx, m), r);
+  int32_t y0 = floored_mod(f2i(fy, m), q), y1 = floored_mod(f2i(cy, m), q);
+  uint32_t i1 = fso_mix(cx - x, cm[(size_t)y0 * r + x0], x - fx, cm[(size_t)y0 * r + x1]);
+  uint32_t i2 = fso_mix(cx - x, cm[(size_t)y1 * r + x0], x - fx, cm[(size_t)y1 * r + x1]);
+  return fso_mix(cy - y, i1, y - fy, i2);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Renderer constants
+ * ---------------------------------------------------------------------------------------- */
+void fso_params_default(fso_params *p) {
+  p->z0 = 0.0f;            /* fut/voxel_renderer.fut:103 */
+  p->delta = 0.001f;       /* :104 */
+  p->invz_param1 = 1.0f;   /* :217 */
+  p->invz_param2 = 0.0f;   /* => f32(w/2), :217 */
+  p->filter = FSO_FILTER_BILINEAR;  /* fut/interactive.fut:180-181 */
+  p->sentinel = FSO_SENTINEL_ZERO;  /* fut/voxel_renderer.fut:244-248 */
+  p->f2i_mode = FSO_F2I_SATURATE;   /* default backend opencl, Makefile:4 */
+  p->reserved = 0;
+}
+void fso_params_tests_variant(fso_params *p) {
+  p->z0 = 1.0f;            /* tests/futspace.fut:84 */
+  p->delta = 0.005f;       /* :85 */
+  p->invz_param1 = 1.0f;
+  p->invz_param2 = 240.0f; /* :91 */
+  p->filter = FSO_FILTER_NEAREST;   /* :76-79, :95-96 */
+  p->sentinel = FSO_SENTINEL_SKY;   /* :110-121 */
+  p->f2i_mode = FSO_F2I_SATURATE;
+  p->reserved = 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * get_zs  fut/voxel_renderer.fut:28-34 (called :108 as get_zs c.distance 0.001 0.0)
+ * same series: tests/futspace.fut:47-53, tests/solve_arithm.fut:1-8
+ * ---------------------------------------------------------------------------------------- */
+static int zs_count(float delta, float dist, float z0) {
+  float t = delta - 2.0f * z0;
+  float e = 8.0f * delta;
+  e = e * dist;
+  float s = sqrtf(powf(t, 2.0f) + e);
+  float num = s - 2.0f * z0;
+  num = num + delta;
+  float div = 2.0f * delta;
+  float nf = floorf(num / div);
+  if (!(nf == nf) || nf > 1.0e8f) return -1;
+  if (nf < 0.0f) return -1; /* futhark: `1...n` with n < 0 is a range error */
+  return (int)nf;
+}
+static inline float zs_value(int i1, float delta, float z0) { /* i1 = 1..n */
+  float i = (float)i1;
+  float a = i / 2.0f;
+  float b = 2.0f * z0;
+  float c = (i - 1.0f) * delta;
+  return a * (b + c);
+}
+int fso_get_zs(float delta, float dist, float z0, float *out, int cap) {
+  int n = zs_count(delta, dist, z0);
+  if (n < 0) return -1;
+  for (int i = 1; i <= n && i <= cap; ++i) out[i - 1] = zs_value(i, delta, z0);
+  return n;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Per-depth line set-up: get_h_line fut/voxel_renderer.fut:43-60 and inv_z :217
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { float sx, sy, dx, dy, inv_z; } depth_line;
+
+static void make_line(const fso_camera *c, const fso_params *p, float z, int w, depth_line *l) {
+  float sin_ang = sinf(c->angle), cos_ang = cosf(c->angle);
+  float view = c->fov;
+  float sv = sin_ang * view, cv = cos_ang * view;
+  float left_x = (-cos_ang - sv) * z;
+  float left_y = (sin_ang - cv) * z;
+  float right_x = (cos_ang - sv) * z;
+  float right_y = (-sin_ang - cv) * z;
+  l->dx = (right_x - left_x) / (float)w;
+  l->dy = (right_y - left_y) / (float)w;
+  l->sx = left_x + c->x;
+  l->sy = left_y + c->y;
+  float mul = p->invz_param2 > 0.0f ? p->invz_param2 : (float)(w / 2);
+  l->inv_z = (p->invz_param1 / z) * mul;
+}
+
+static depth_line *make_lines(const fso_camera *c, const fso_params *p, int w, int *n_out) {
+  int n = zs_count(p->delta, c->distance, p->z0);
+  if (n < 0) return NULL;
+  depth_line *L = (depth_line *)malloc(sizeof(depth_line) * (size_t)(n > 0 ? n : 1));
+  if (!L) return NULL;
+  for (int k = 0; k < n; ++k) make_line(c, p, zs_value(k + 1, p->delta, p->z0), w, &L[k]);
+  *n_out = n;
+  return L;
+}
+
+/* one (colour, y) sample: fut/voxel_renderer.fut:219-226 */
+static inline int32_t project(const fso_camera *c, const fso_params *p, const depth_line *l, float hgt) {
+  float height_diff = c->height - hgt;
+  float t = height_diff * l->inv_z;
+  float rel = t + c->horizon;
+  int32_t y = f2i(rel, p->f2i_mode);
+  return y > 0 ? y : 0;
+}
+static inline void seg_point(const depth_line *l, int i, float *x, float *y) { /* :63-66 */
+  float fi = (float)i;
+  float a = fi * l->dx, b = fi * l->dy;
+  *x = l->sx + a;
+  *y = l->sy + b;
+}
+
+static int check_args(const fso_camera *cam, const fso_params *prm, const void *a, const void *b, int q,
+                      int r, int h, int w, const void *out) {
+  if (!cam || !prm || !a || !b || !out) return 1;
+  if (q <= 0 || r <= 0 || h <= 0 || w <= 0) return 2;
+  return 0;
+}
+
+int fso_render(const fso_camera *cam, const fso_params *prm, const uint32_t *color, const int32_t *height,
+               int q, int r, int h, int w, uint32_t *out, int eval_all, int nthreads) {
+  int rc = check_args(cam, prm, color, height, q, r, h, w, out);
+  if (rc) return rc;
+  int n = 0;
+  depth_line *L = make_lines(cam, prm, w, &n);
+  if (!L) return 3;
+  const int bil = prm->filter == FSO_FILTER_BILINEAR, m = prm->f2i_mode;
+  const uint32_t empty = prm->sentinel == FSO_SENTINEL_SKY ? cam->sky_color : 0u;
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+  (void)nthreads;
+#endif
+#pragma omp parallel num_threads(nthreads)
+  {
+    uint32_t *col = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)h);
+#pragma omp for schedule(dynamic, 4)
+    for (int j = 0; j < w; ++j) {
+      for (int i = 0; i < h; ++i) col[i] = empty;
+      int32_t ybuf = h;
+      for (int k = 0; k < n; ++k) {
+        float x, y;
+        seg_point(&L[k], j, &x, &y);
+        float hgt = bil ? fso_height_bilinear(height, q, r, x, y, m) : fso_height_nearest(height, q, r, x, y, m);
+        uint32_t c = 0;
+        if (eval_all) c = bil ? fso_color_bilinear(color, q, r, x, y, m) : fso_color_nearest(color, q, r, x, y, m);
+        int32_t yy = project(cam, prm, &L[k], hgt);
+        if (yy < ybuf) {
+          if (!eval_all) c = bil ? fso_color_bilinear(color, q, r, x, y, m) : fso_color_nearest(color, q, r, x, y, m);
+          col[yy] = c;
+          ybuf = yy;
+        }
+      }
+      uint32_t carry = empty;
+      for (int i = 0; i < h; ++i) {
+        if (col[i] != empty) carry = col[i];
+        out[(size_t)i * w + j] = carry == empty ? cam->sky_color : carry;
+      }
+    }
+    free(col);
+  }
+  free(L);
+  return 0;
+}
+
+int fso_render_literal(const fso_camera *cam, const fso_params *prm, const uint32_t *color,
+                       const int32_t *height, int q, int r, int h, int w, uint32_t *out) {
+  int rc = check_args(cam, prm, color, height, q, r, h, w, out);
+  if (rc) return rc;
+  int n = 0;
+  depth_line *L = make_lines(cam, prm, w, &n);
+  if (!L) return 3;
+  const int bil = prm->filter == FSO_FILTER_BILINEAR, m = prm->f2i_mode;
+  const uint32_t empty = prm->sentinel == FSO_SENTINEL_SKY ? cam->sky_color : 0u;
+  size_t cells = (size_t)(n > 0 ? n : 1) * (size_t)w;
+  uint32_t *cs = (uint32_t *)malloc(cells * 4);
+  int32_t *hs = (int32_t *)malloc(cells * 4);
+  uint32_t *col = (uint32_t *)malloc((size_t)h * 4);
+  if (!cs || !hs || !col) { free(cs); free(hs); free(col); free(L); return 3; }
+  /* height_color_map, :215-228 : [n_z][w] */
+  for (int k = 0; k < n; ++k)
+    for (int i = 0; i < w; ++i) {
+      float x, y;
+      seg_point(&L[k], i, &x, &y);
+      uint32_t c = bil ? fso_color_bilinear(color, q, r, x, y, m) : fso_color_nearest(color, q, r, x, y, m);
+      float hgt = bil ? fso_height_bilinear(height, q, r, x, y, m) : fso_height_nearest(height, q, r, x, y, m);
+      cs[(size_t)k * w + i] = c;
+      hs[(size_t)k * w + i] = project(cam, prm, &L[k], hgt);
+    }
+  /* rendered_image, :229-250, over (transpose height_color_map) */
+  for (int j = 0; j < w; ++j) {
+    /* scan occlude (0,h) : inclusive; res[0] = xs[0] */
+    uint32_t ac = 0; int32_t ah = 0;
+    for (int i = 0; i < h; ++i) col[i] = empty;  /* replicate h 0 | replicate l sky */
+    for (int k = 0; k < n; ++k) {
+      uint32_t c2 = cs[(size_t)k * w + j]; int32_t h2 = hs[(size_t)k * w + j];
+      if (k == 0 || !(ah <= h2)) { ac = c2; ah = h2; }  /* occlude :69-72 */
+      if (ah >= 0 && ah < h) col[ah] = ac;              /* scatter :244 ignores out-of-range */
+    }
+    /* scan fill_vline 0 :246 ; fill :110-113 in the sentinel variant */
+    uint32_t acc = 0;
+    for (int i = 0; i < h; ++i) {
+      acc = (i == 0) ? col[0] : (col[i] == empty ? acc : col[i]);
+      /* :248 sky map (identity in the sky-sentinel variant) */
+      out[(size_t)i * w + j] = (prm->sentinel == FSO_SENTINEL_ZERO && acc == 0u) ? cam->sky_color : acc;
+    }
+  }
+  free(cs); free(hs); free(col); free(L);
+  return 0;
+}
+
+void fso_mask_heights(int32_t *hm, long n) { /* fut/interactive.fut:189 */
+  for (long i = 0; i < n; ++i) hm[i] &= 0xFF;
+}
