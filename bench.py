@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the futspace render hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k|cfg1] [--impl ours|reference]
+
+One "step" = one camera-path batch of `poses` frames rendered through the C-ABI
+(fsb_render_batch_device for `value`: frames stay in HBM; fsb_render_batch for `e2e`: pinned host
+frames, H2D pose constants + D2H frames inside the timed region).  N > 1: one process per GPU
+(torchrun), the global camera path is sharded frame-parallel, no data-path collective; time is the
+max over ranks of the CUDA-event time on each rank's launch stream.
+
+--impl reference times the CPU restatement of the reference (oracle/, OpenMP over columns, colour
+evaluated for every sample as the reference does) on the host cores: the reference itself cannot be
+built here (Futhark + un-vendored packages, DESIGN.md "Oracle").
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SKY = 0xFF9090E0
+WORKLOADS = {
+    # BASELINE.json configs[1] (+ configs[3]: the same frame as a 512-pose camera path)
+    "1080p": dict(map=2048, w=1920, h=1080, dist=2000.0, poses=512, ref_poses=32,
+                  name="1920x1080, 2048^2 synthetic fBm terrain, draw distance 2000, 512-pose camera path per GPU"),
+    # BASELINE.json configs[2]
+    "4k": dict(map=4096, w=3840, h=2160, dist=4000.0, poses=64, ref_poses=8,
+               name="3840x2160, 4096^2 synthetic fBm terrain, draw distance 4000, 64-pose camera path per GPU"),
+    # BASELINE.json configs[0] (synthetic stand-in for the converted map pair)
+    "cfg1": dict(map=1024, w=1024, h=768, dist=1000.0, poses=512, ref_poses=64,
+                 name="1024x768, 1024^2 synthetic fBm terrain, draw distance 1000, 512-pose camera path per GPU"),
+}
+
+
+def camera_path(F_or_O, height_map, m, n_total, first, count, h, dist):
+    """SURVEY.md 8d path; camera height clamped to terrain + 20 as terrain_collision would (fut/interactive.fut:67-87)."""
+    cams = []
+    for i in range(first, first + count):
+        th = 2.0 * math.pi * i / n_total
+        x = m / 2 + (m / 4) * math.cos(th)
+        y = m / 2 + (m / 4) * math.sin(th)
+        ground = float(height_map[int(y) % m, int(x) % m])
+        hgt = max(160.0 + 40.0 * math.sin(2 * th), ground + 20.0)
+        cams.append(F_or_O.Camera(x, y, hgt, 2.2 + th, 0.3 * h, dist, 1.2, SKY))
+    return cams
+
+
+def n_z_of(F, prm, dist):
+    return len(F.get_zs(prm.delta, dist, prm.z0))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the march kernel from the committed ncu capture, if any (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(workload)
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, wl):
+    """CPU arm: the oracle (C restatement of the reference) on all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import futspace_b200 as F   # terrain generator + z-series only (host functions, no GPU)
+    m, w, h, dist = wl["map"], wl["w"], wl["h"], wl["dist"]
+    col, hgt = F.terrain_fbm(m)
+    prm = O.default_params()
+    n_ref = wl["ref_poses"]
+    total = wl["poses"] * max(1, args.gpus)
+    cores = os.cpu_count()
+    # the sample: n_ref poses evenly spaced over the global path, a different offset each step
+    def step(s):
+        idx = [((s * 7 + j * (total // n_ref)) % total) for j in range(n_ref)]
+        for i in idx:
+            cam = camera_path(O, hgt, m, total, i, 1, h, dist)[0]
+            O.render(cam, prm, col, hgt, h, w, eval_all_colors=True, nthreads=0)
+    for s in range(args.warmup):
+        step(s)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step(args.warmup + s)
+    dt = time.perf_counter() - t0
+    fps = n_ref * args.steps / dt
+    out = {
+        "impl": "reference", "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "frame": [w, h], "map": m, "distance": dist, "filter": "bilinear",
+                   "poses_per_step": n_ref},
+        "mpixel_per_s": fps * w * h / 1e6,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d of the %d path poses per step, C restatement of the reference (oracle/), "
+                                   "OpenMP over columns, colour filter evaluated for every sample" % (n_ref, total)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def time_device_steps(torch, ctx, st, fn, steps, flush):
+    """-> list of per-step milliseconds (CUDA events on the launching stream); L2 flushed between steps."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        if flush is not None:
+            with torch.cuda.stream(st):
+                flush.add_(1)
+        a.record(st)
+        fn()
+        b.record(st)
+    ctx.sync()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def run_ours(args, wl):
+    import torch
+    import futspace_b200 as F
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(1, args.gpus):
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d (one process per GPU)" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    m, w, h, dst, P = wl["map"], wl["w"], wl["h"], wl["dist"], wl["poses"]
+    if args.poses:
+        P = args.poses
+    col, hgt = F.terrain_fbm(m)
+    ctx = F.Context(local)
+    mp = ctx.upload_map(col, hgt)
+    prm = F.default_params()
+    nz = n_z_of(F, prm, dst)
+    total = P * world
+    cams = camera_path(F, hgt, m, total, rank * P, P, h, dst)
+    cam_arr = (F.Camera * P)(*cams)
+    frame_bytes = w * h * 4
+    st = torch.cuda.ExternalStream(ctx.stream)
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    out_dev = ctx.device_malloc(P * frame_bytes)
+
+    def step_dev():
+        ctx.render_batch_device(cam_arr, prm, mp, h, w, out_dev)
+
+    # ---- value: device-resident frames ----
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    ctx.sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = ctx.launch_count
+    ms = time_device_steps(torch, ctx, st, step_dev, args.steps, flush)
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop()
+    barrier()
+    total_ms = max_over_ranks(sum(ms))
+    value = total * args.steps / (total_ms / 1e3)
+
+    # ---- per-kernel share + roofline of the dominant kernel (march) ----
+    ctx.set_profiling(True)
+    step_dev()
+    ctx.get_profile()
+    for _ in range(2):
+        step_dev()
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    march_ms, march_n = prof["march"]
+    expand_ms, expand_n = prof["expand"]
+    setup_ms, setup_n = prof["setup"]
+    poses_per_launch = 2.0 * P / march_n
+    gather_bytes = 4.0 * 4 * w * nz                    # 4 taps x 4 B packed texel per sample
+    frame_alg = 4.0 * w * h
+    peak, peak_src = measured_peaks()
+    achieved = gather_bytes * poses_per_launch / (march_ms / march_n * 1e-3) / 1e9
+    tr = ncu_traffic(args.workload)
+    roofline = {"bound": "hbm", "kernel": "fsb_march_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": gather_bytes * poses_per_launch,
+                "launch_ms": march_ms / march_n,
+                "kernel_share_of_step": march_ms / (march_ms + expand_ms + setup_ms)}
+    step_alg = (gather_bytes + frame_alg) * P
+    roofline_step = {"achieved": step_alg / (total_ms / args.steps * 1e-3) / 1e9, "unit": "GB/s per GPU",
+                     "frac": step_alg / (total_ms / args.steps * 1e-3) / 1e9 / peak,
+                     "algorithmic_bytes_per_step_per_gpu": step_alg,
+                     "kernel_ms_per_step": {"setup": setup_ms / 2, "march": march_ms / 2, "expand": expand_ms / 2}}
+
+    # ---- e2e: host frames through fsb_render_batch (pinned), copies inside the timed region ----
+    host = ctx.host_malloc(P * frame_bytes)
+
+    def step_e2e():
+        ctx.render_batch(cam_arr, prm, mp, h, w, out=host)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        step_e2e()
+    ctx.sync()
+    e_dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = total * e_steps / e_dt
+    e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 64 * P, "d2h_bytes_per_step": P * frame_bytes,
+           "steps": e_steps, "ms_per_step": 1e3 * e_dt / e_steps,
+           "api": "fsb_render_batch (pinned host frames; pose constants H2D + frames D2H inside the timed region)"}
+
+    extra = {}
+    cpu = None
+    if rank == 0:
+        extra["l2_stream_gbs"] = ctx.l2_stream_gbs()
+        extra["l2_gather_gsectors"] = ctx.l2_gather_gsectors()
+        taps_per_s = 4.0 * w * nz * poses_per_launch / (march_ms / march_n * 1e-3)
+        extra["l2_gather_roofline_frac"] = taps_per_s / (extra["l2_gather_gsectors"] * 1e9)
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline(F, wl, col, hgt, total)
+    ctx.host_free(host)
+    ctx.device_free(out_dev)
+    mp.free()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    out = {
+        "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "frame": [w, h], "map": m, "distance": dst, "n_z": nz,
+                   "filter": "bilinear", "poses_per_gpu_per_step": P, "global_poses_per_step": total,
+                   "parallelism": "frame-parallel x%d, maps replicated, no collective" % world,
+                   "l2": "256 MiB scratch write between timed steps (flush); each step also streams %.1f GB of "
+                         "frames through the 126 MB L2; the %d MiB packed map is L2-resident by design"
+                         % (P * frame_bytes / 1e9, m * m * 4 >> 20)},
+        "mpixel_per_s": value * w * h / 1e6,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_step": roofline_step,
+        "cpu_baseline": cpu,
+    }
+    out.update(extra)
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(F, wl, col, hgt, total):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    m, w, h, dst = wl["map"], wl["w"], wl["h"], wl["dist"]
+    prm = O.default_params()
+    cam0 = camera_path(O, hgt, m, total, 0, 1, h, dst)[0]
+    O.render(cam0, prm, col, hgt, h, w, eval_all_colors=True, nthreads=0)   # warm-up
+    # bounded sample: poses spread over the path (stride 37 is coprime to the path length) until ~12 s of CPU work
+    t0 = time.perf_counter()
+    n = 0
+    while n < total and time.perf_counter() - t0 < 12.0:
+        i = (n * 37) % total
+        O.render(camera_path(O, hgt, m, total, i, 1, h, dst)[0], prm, col, hgt, h, w, eval_all_colors=True, nthreads=0)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d poses spread over the %d-pose path (%.1f s), C restatement of the reference (oracle/), "
+                      "OpenMP over columns, colour filter evaluated for every sample as the reference does" % (n, total, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--poses", type=int, default=0, help="override poses per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,8 @@ SYMBOLS = {
     "fsb_context_stream": (_vp, [_vp]),
     "fsb_context_launch_count": (ctypes.c_int64, [_vp]),
     "fsb_context_device_name": (_ci, [_vp, ctypes.c_char_p, _sz]),
+    "fsb_context_set_profiling": (_ci, [_vp, _ci]),
+    "fsb_context_get_profile": (_ci, [_vp, _P(ctypes.c_double), _P(ctypes.c_int64)]),
     "fsb_params_default": (None, [_P(Params)]),
     "fsb_params_tests_variant": (None, [_P(Params)]),
     "fsb_get_zs": (_ci, [_cf, _cf, _cf, _vp, _ci]),
@@ -196,6 +198,16 @@ class Context:
         lib().fsb_context_device_name(self.handle, b, 128)
         return b.value.decode()
 
+    def set_profiling(self, enable):
+        self._check(lib().fsb_context_set_profiling(self.handle, 1 if enable else 0))
+
+    def get_profile(self):
+        """-> {"setup"|"march"|"expand": (total_ms, launches)} since the last call."""
+        ms = (ctypes.c_double * 3)()
+        n = (ctypes.c_int64 * 3)()
+        self._check(lib().fsb_context_get_profile(self.handle, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(("setup", "march", "expand"))}
+
     def upload_map(self, color, height, mask_heights=True):
         color = np.ascontiguousarray(color, dtype=np.uint32)
         height = np.ascontiguousarray(height, dtype=np.int32)
@@ -215,11 +227,11 @@ class Context:
         return out
 
     def render_batch(self, cams, prm, mp, h, w, out=None):
-        arr = (Camera * len(cams))(*cams)
+        arr = cams if isinstance(cams, ctypes.Array) else (Camera * len(cams))(*cams)
         if out is None:
-            out = np.empty((len(cams), h, w), np.uint32)
+            out = np.empty((len(arr), h, w), np.uint32)
         ptr = out if isinstance(out, int) else out.ctypes.data
-        self._check(lib().fsb_render_batch(self.handle, arr, len(cams), ctypes.byref(prm), mp.handle, h, w, ptr))
+        self._check(lib().fsb_render_batch(self.handle, arr, len(arr), ctypes.byref(prm), mp.handle, h, w, ptr))
         return out
 
     def render_device(self, cam, prm, mp, h, w, out_dev, row_stride=0):

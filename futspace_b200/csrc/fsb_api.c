@@ -34,6 +34,14 @@ struct fsb_context {
   size_t tab_cap;                 /* entries */
   uint32_t *frame_dev[2];
   size_t frame_cap[2];            /* pixels */
+  int profiling;
+  cudaEvent_t pev[4];             /* profiling: before set-up, after set-up, after march, after expand */
+  double prof_ms[3];
+  int64_t prof_n[3];
+  int prof_pending;
+  void *recs;                     /* march -> expand record lists */
+  uint32_t *sidx;
+  size_t recs_cap, sidx_cap;      /* bytes */
   char name[128];
 };
 
@@ -170,7 +178,11 @@ void fsb_context_free(fsb_context *ctx) {
   cudaFree(ctx->invz);
   cudaFree(ctx->frame_dev[0]);
   cudaFree(ctx->frame_dev[1]);
+  cudaFree(ctx->recs);
+  cudaFree(ctx->sidx);
   cudaEventDestroy(ctx->fc_free);
+  for (int i = 0; i < 4; ++i)
+    if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
   for (int i = 0; i < 2; ++i) {
     cudaEventDestroy(ctx->rendered[i]);
     cudaEventDestroy(ctx->copied[i]);
@@ -282,6 +294,39 @@ static int ensure_tables(fsb_context *ctx, int n_poses, int zstride) {
   return FSB_OK;
 }
 
+#define FSB_RB_SHIFT 8                   /* expand band = 256 rows */
+#define FSB_MAX_H 32768
+#define FSB_SCRATCH_BUDGET ((size_t)768 << 20)
+
+static int ensure_scratch(fsb_context *ctx, int n_poses, int ncols, int h) {
+  const int n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
+  const size_t need_r = (size_t)n_poses * ncols * h * 8, need_s = (size_t)n_poses * ncols * (n_bands + 1) * 4;
+  if (need_r > ctx->recs_cap) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->recs);
+    ctx->recs = NULL; ctx->recs_cap = 0;
+    CU(ctx, cudaMalloc(&ctx->recs, need_r));
+    ctx->recs_cap = need_r;
+  }
+  if (need_s > ctx->sidx_cap) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->sidx);
+    ctx->sidx = NULL; ctx->sidx_cap = 0;
+    CU(ctx, cudaMalloc((void **)&ctx->sidx, need_s));
+    ctx->sidx_cap = need_s;
+  }
+  return FSB_OK;
+}
+
+/* poses per launch group: bounded by the record-list scratch budget */
+static int group_size(int n, int ncols, int h) {
+  size_t per = (size_t)ncols * h * 8;
+  size_t g = FSB_SCRATCH_BUDGET / (per ? per : 1);
+  if (g < 1) g = 1;
+  if (g > FSB_MAX_POSES_PER_LAUNCH) g = FSB_MAX_POSES_PER_LAUNCH;
+  return (size_t)n < g ? n : (int)g;
+}
+
 static int check_common(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm, const fsb_map *map,
                         int h, int w, int col_begin, int col_end, const void *out) {
   if (!ctx) return FSB_ERR_ARG;
@@ -290,9 +335,44 @@ static int check_common(fsb_context *ctx, const fsb_camera *cams, int n, const f
     return set_err(ctx, FSB_ERR_ARG, "render: bad sizes n=%d h=%d w=%d cols=[%d,%d)", n, h, w, col_begin, col_end);
   if ((unsigned)prm->filter > 1u || (unsigned)prm->sentinel > 1u || (unsigned)prm->f2i_mode > 2u)
     return set_err(ctx, FSB_ERR_ARG, "render: unknown filter/sentinel/f2i_mode");
-  if (fsb_render_smem_bytes(h, 8) > ctx->max_smem_optin)
-    return set_err(ctx, FSB_ERR_RANGE, "render: frame height %d needs %d B of shared memory per CTA (limit %d)", h,
-                   fsb_render_smem_bytes(h, 8), ctx->max_smem_optin);
+  if (h > FSB_MAX_H) return set_err(ctx, FSB_ERR_RANGE, "render: frame height %d exceeds the limit %d", h, FSB_MAX_H);
+  return FSB_OK;
+}
+
+/* profiling: fold the event deltas of the previous launch group into the accumulators */
+static int prof_collect(fsb_context *ctx) {
+  if (!ctx->prof_pending) return FSB_OK;
+  CU(ctx, cudaEventSynchronize(ctx->pev[3]));
+  for (int i = 0; i < 3; ++i) {
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, ctx->pev[i], ctx->pev[i + 1]));
+    ctx->prof_ms[i] += ms;
+    ctx->prof_n[i] += 1;
+  }
+  ctx->prof_pending = 0;
+  return FSB_OK;
+}
+
+int fsb_context_set_profiling(fsb_context *ctx, int enable) {
+  if (!ctx) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (enable && !ctx->pev[0])
+    for (int i = 0; i < 4; ++i) CU(ctx, cudaEventCreate(&ctx->pev[i]));
+  int rc = prof_collect(ctx);
+  ctx->profiling = enable != 0;
+  return rc;
+}
+
+int fsb_context_get_profile(fsb_context *ctx, double *ms, int64_t *launches) {
+  if (!ctx || !ms || !launches) return FSB_ERR_ARG;
+  int rc = prof_collect(ctx);
+  if (rc) return rc;
+  for (int i = 0; i < 3; ++i) {
+    ms[i] = ctx->prof_ms[i];
+    launches[i] = ctx->prof_n[i];
+    ctx->prof_ms[i] = 0.0;
+    ctx->prof_n[i] = 0;
+  }
   return FSB_OK;
 }
 
@@ -319,15 +399,23 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
       if (ctx->fc_host[i].n_z > max_nz) max_nz = ctx->fc_host[i].n_z;
     }
   }
-  const int zstride = max_nz > 0 ? (max_nz + 31) & ~31 : 32;
+  /* the march loop prefetches up to three chunks past the last one (fsb_kernels.cu) */
+  const int zstride = ((max_nz + 31) & ~31) + 96;
   if ((rc = ensure_tables(ctx, n, zstride))) return rc;
+  if ((rc = ensure_scratch(ctx, n, col_end - col_begin, h))) return rc;
   if (n > 1) {
     CU(ctx, cudaMemcpyAsync(ctx->fc_dev, ctx->fc_host, sizeof(fsb_frame_consts) * (size_t)n, cudaMemcpyHostToDevice,
                             ctx->stream));
     CU(ctx, cudaEventRecord(ctx->fc_free, ctx->stream));
   }
+  if (ctx->profiling) {
+    int prc = prof_collect(ctx);
+    if (prc) return prc;
+    CU(ctx, cudaEventRecord(ctx->pev[0], ctx->stream));
+  }
   CU(ctx, (cudaError_t)fsb_launch_setup(ctx->fc_dev, n == 1 ? &single : NULL, n, max_nz, ctx->lines, ctx->invz,
                                         zstride, ctx->stream, &ctx->launches));
+  if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[1], ctx->stream));
   fsb_render_args a;
   memset(&a, 0, sizeof a);
   a.packed = map->packed;
@@ -350,9 +438,20 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.filter = prm->filter;
   a.f2i_mode = prm->f2i_mode;
   a.alpha_bits = map->alpha_bits;
+  a.recs = (uint2_fsb *)ctx->recs;
+  a.sidx = ctx->sidx;
+  a.rec_cap = h;
+  a.rb_shift = FSB_RB_SHIFT;
+  a.n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
   const int use_packed = map->packed && map->pow2 && prm->f2i_mode == FSB_F2I_SATURATE &&
                          !(prm->flags & FSB_FLAG_FORCE_GENERIC);
-  CU(ctx, (cudaError_t)fsb_launch_render(&a, use_packed, ctx->stream, &ctx->launches));
+  CU(ctx, (cudaError_t)fsb_launch_march(&a, use_packed, ctx->stream, &ctx->launches));
+  if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
+  CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));
+  if (ctx->profiling) {
+    CU(ctx, cudaEventRecord(ctx->pev[3], ctx->stream));
+    ctx->prof_pending = 1;
+  }
   return FSB_OK;
 }
 
@@ -378,8 +477,9 @@ int fsb_render_batch_device(fsb_context *ctx, const fsb_camera *cams, int n, con
   if (rc) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   const int64_t frame = (int64_t)h * w;
-  for (int i = 0; i < n; i += FSB_MAX_POSES_PER_LAUNCH) {
-    int c = n - i < FSB_MAX_POSES_PER_LAUNCH ? n - i : FSB_MAX_POSES_PER_LAUNCH;
+  const int g = group_size(n, w, h);
+  for (int i = 0; i < n; i += g) {
+    int c = n - i < g ? n - i : g;
     if ((rc = render_poses(ctx, cams + i, c, prm, map, h, w, 0, w, out_dev + (size_t)i * frame, w, frame))) return rc;
   }
   return FSB_OK;
@@ -414,6 +514,7 @@ int fsb_render_batch(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_
   size_t chunk = (64u << 20) / (frame * 4);
   if (chunk < 1) chunk = 1;
   if (chunk > (size_t)n) chunk = (size_t)n;
+  if (chunk > (size_t)group_size(n, w, h)) chunk = (size_t)group_size(n, w, h);
   const int nbuf = (size_t)n > chunk ? 2 : 1;
   for (int s = 0; s < nbuf; ++s)
     if ((rc = ensure_frame(ctx, s, chunk * frame))) return rc;

@@ -21,6 +21,12 @@ typedef struct fsb_frame_consts {
   uint32_t sky, empty;          /* empty = 0 (zero sentinel) or sky (sky sentinel) */
 } fsb_frame_consts;
 
+#ifdef __CUDACC__
+typedef uint2 uint2_fsb;
+#else
+typedef struct { uint32_t x, y; } uint2_fsb;
+#endif
+
 typedef struct fsb_render_args {
   const uint32_t *packed;   /* [q][r] height<<24 | rgb, or NULL */
   const uint32_t *color;    /* [q][r] argb  */
@@ -38,6 +44,11 @@ typedef struct fsb_render_args {
   int32_t n_poses;
   int32_t filter, f2i_mode;
   uint32_t alpha_bits;      /* packed maps: the map-uniform alpha byte << 24 */
+  /* march -> expand hand-off (device scratch, L2-resident in steady state) */
+  uint2_fsb *recs;          /* [n_poses][ncols][rec_cap] {row, colour}: visible samples front to back  */
+  uint32_t *sidx;           /* [n_poses][ncols][n_bands+1]: sidx[b] = #records with row >= b<<rb_shift */
+  int32_t rec_cap;          /* = h (rows strictly decrease along a list)                               */
+  int32_t n_bands, rb_shift;
 } fsb_render_args;
 
 /* launchers implemented in fsb_kernels.cu; stream is a cudaStream_t passed as void*.
@@ -46,8 +57,8 @@ typedef struct fsb_render_args {
  * by the kernel); otherwise fc_dev[n_poses] must already be in device memory. */
 int fsb_launch_setup(const fsb_frame_consts *fc_dev, const fsb_frame_consts *single, int n_poses, int max_nz,
                      float *lines, float *invz, int zstride, void *stream, int64_t *launches);
-int fsb_launch_render(const fsb_render_args *a, int use_packed, void *stream, int64_t *launches);
-int fsb_render_smem_bytes(int h, int tw);
+int fsb_launch_march(const fsb_render_args *a, int use_packed, void *stream, int64_t *launches);
+int fsb_launch_expand(const fsb_render_args *a, void *stream, int64_t *launches);
 int fsb_launch_l2_stream(const uint32_t *buf, size_t n_words, uint32_t *sink, int blocks, void *stream);
 int fsb_launch_l2_gather(const uint32_t *buf, size_t n_sectors, uint32_t *sink, int blocks, int per_thread,
                          void *stream);
