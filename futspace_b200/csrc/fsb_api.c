@@ -30,8 +30,8 @@ struct fsb_context {
   int max_smem_optin, sm_count;
   fsb_frame_consts *fc_dev, *fc_host;
   int fc_cap;
-  float *lines, *invz;
-  size_t tab_cap;                 /* entries */
+  float *table;                   /* per-pose depth tables (blocked by chunk, fsb_kernels.cu) */
+  size_t tab_cap;                 /* floats */
   uint32_t *frame_dev[2];
   size_t frame_cap[2];            /* pixels */
   int profiling;
@@ -49,7 +49,7 @@ struct fsb_map {
   uint32_t *packed, *color;
   int32_t *height;
   int q, r;
-  int pow2;
+  int pow2, log2r;
   uint32_t alpha_bits;
 };
 
@@ -174,8 +174,7 @@ void fsb_context_free(fsb_context *ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   cudaFree(ctx->fc_dev);
   cudaFreeHost(ctx->fc_host);
-  cudaFree(ctx->lines);
-  cudaFree(ctx->invz);
+  cudaFree(ctx->table);
   cudaFree(ctx->frame_dev[0]);
   cudaFree(ctx->frame_dev[1]);
   cudaFree(ctx->recs);
@@ -229,14 +228,20 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   m->q = q;
   m->r = r;
   m->pow2 = ((q & (q - 1)) == 0) && ((r & (r - 1)) == 0);
+  while ((1 << m->log2r) < r) ++m->log2r;
   /* update_map, fut/interactive.fut:189: altitude = height & 0xFF */
-  int packable = 1;
+  /* the packed fast path needs power-of-two sizes holding at least one 8x4 tile (fsb_kernels.cu texel_x/texel_y) */
+  int packable = m->pow2 && r >= 8 && q >= 4;
   const uint32_t alpha = color[0] & 0xFF000000u;
   for (size_t i = 0; i < n; ++i) {
     int32_t hv = mask_heights ? (height[i] & 0xFF) : height[i];
     hm[i] = hv;
     if (hv < 0 || hv > 255 || (color[i] & 0xFF000000u) != alpha) packable = 0;
-    pk[i] = ((uint32_t)hv << 24) | (color[i] & 0x00FFFFFFu);
+    if (m->pow2 && r >= 8 && q >= 4) {
+      const size_t y = i / (size_t)r, x = i % (size_t)r;
+      const size_t t = ((y >> 2) * (size_t)(r >> 3) + (x >> 3)) * 32 + ((y & 3) << 3) + (x & 7);
+      pk[t] = ((uint32_t)hv << 24) | (color[i] & 0x00FFFFFFu);
+    }
   }
   m->alpha_bits = alpha;
   cudaError_t e = cudaMalloc((void **)&m->color, n * 4);
@@ -272,7 +277,7 @@ int fsb_map_free(fsb_context *ctx, fsb_map *m) {
 int fsb_map_is_packed(const fsb_map *m) { return m && m->packed != NULL; }
 
 /* ------------------------------------------------------------------------------------------ */
-static int ensure_tables(fsb_context *ctx, int n_poses, int zstride) {
+static int ensure_tables(fsb_context *ctx, int n_poses, int tab_stride) {
   if (n_poses > ctx->fc_cap) {
     cudaFree(ctx->fc_dev);
     cudaFreeHost(ctx->fc_host);
@@ -281,14 +286,12 @@ static int ensure_tables(fsb_context *ctx, int n_poses, int zstride) {
     CU(ctx, cudaMallocHost((void **)&ctx->fc_host, sizeof(fsb_frame_consts) * (size_t)n_poses));
     ctx->fc_cap = n_poses;
   }
-  const size_t need = (size_t)n_poses * (size_t)zstride;
+  const size_t need = (size_t)n_poses * (size_t)tab_stride;
   if (need > ctx->tab_cap) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->lines);
-    cudaFree(ctx->invz);
-    ctx->lines = NULL; ctx->invz = NULL; ctx->tab_cap = 0;
-    CU(ctx, cudaMalloc((void **)&ctx->lines, need * 16));
-    CU(ctx, cudaMalloc((void **)&ctx->invz, need * 4));
+    cudaFree(ctx->table);
+    ctx->table = NULL; ctx->tab_cap = 0;
+    CU(ctx, cudaMalloc((void **)&ctx->table, need * 4));
     ctx->tab_cap = need;
   }
   return FSB_OK;
@@ -390,7 +393,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   }
   int rc;
   if (n > 1) {
-    if ((rc = ensure_tables(ctx, n, 32))) return rc;
+    if ((rc = ensure_tables(ctx, n, 160))) return rc;
     CU(ctx, cudaEventSynchronize(ctx->fc_free));
     for (int i = 0; i < n; ++i) {
       if (make_consts(&cams[i], prm, w, &ctx->fc_host[i]))
@@ -399,9 +402,9 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
       if (ctx->fc_host[i].n_z > max_nz) max_nz = ctx->fc_host[i].n_z;
     }
   }
-  /* the march loop prefetches up to three chunks past the last one (fsb_kernels.cu) */
-  const int zstride = ((max_nz + 31) & ~31) + 96;
-  if ((rc = ensure_tables(ctx, n, zstride))) return rc;
+  /* depth table: one 160-float block per chunk of 32 samples (fsb_kernels.cu FSB_TAB_BLOCK) */
+  const int tab_stride = 160 * (max_nz > 0 ? (max_nz + 31) / 32 : 1);
+  if ((rc = ensure_tables(ctx, n, tab_stride))) return rc;
   if ((rc = ensure_scratch(ctx, n, col_end - col_begin, h))) return rc;
   if (n > 1) {
     CU(ctx, cudaMemcpyAsync(ctx->fc_dev, ctx->fc_host, sizeof(fsb_frame_consts) * (size_t)n, cudaMemcpyHostToDevice,
@@ -413,8 +416,8 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (prc) return prc;
     CU(ctx, cudaEventRecord(ctx->pev[0], ctx->stream));
   }
-  CU(ctx, (cudaError_t)fsb_launch_setup(ctx->fc_dev, n == 1 ? &single : NULL, n, max_nz, ctx->lines, ctx->invz,
-                                        zstride, ctx->stream, &ctx->launches));
+  CU(ctx, (cudaError_t)fsb_launch_setup(ctx->fc_dev, n == 1 ? &single : NULL, n, ctx->table, tab_stride,
+                                        ctx->stream, &ctx->launches));
   if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[1], ctx->stream));
   fsb_render_args a;
   memset(&a, 0, sizeof a);
@@ -424,9 +427,11 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.q = map->q;
   a.r = map->r;
   a.fc = ctx->fc_dev;
-  a.lines = ctx->lines;
-  a.invz = ctx->invz;
-  a.zstride = zstride;
+  a.table = ctx->table;
+  a.tab_stride = tab_stride;
+  a.xmask_hi = (map->r - 1) & ~7;
+  a.ymask_hi = (map->q - 1) & ~3;
+  a.log2r = map->log2r;
   a.out = out_dev;
   a.row_stride = row_stride;
   a.pose_stride = pose_stride;

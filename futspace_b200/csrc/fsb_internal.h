@@ -28,14 +28,14 @@ typedef struct { uint32_t x, y; } uint2_fsb;
 #endif
 
 typedef struct fsb_render_args {
-  const uint32_t *packed;   /* [q][r] height<<24 | rgb, or NULL */
+  const uint32_t *packed;   /* height<<24 | rgb in 8x4-texel tiles (fsb_kernels.cu texel_x/texel_y), or NULL */
+  int32_t xmask_hi, ymask_hi, log2r; /* tiled addressing: (r-1)&~7, (q-1)&~3, log2(r) */
   const uint32_t *color;    /* [q][r] argb  */
   const int32_t *height;    /* [q][r]       */
   int32_t q, r;
   const fsb_frame_consts *fc; /* device, [n_poses] */
-  const float *lines;       /* device, [n_poses][zstride] float4 {sx, sy, dx, dy}          */
-  const float *invz;        /* device, [n_poses][zstride]                                   */
-  int32_t zstride;
+  const float *table;       /* device, [n_poses][tab_stride]: per chunk of 32 depth samples a 640-byte block */
+  int32_t tab_stride;       /* floats per pose = 160 * number of chunks                                      */
   uint32_t *out;            /* device; pixel (pose 0, row 0, column col_begin)              */
   int64_t row_stride;       /* pixels */
   int64_t pose_stride;      /* pixels */
@@ -55,8 +55,8 @@ typedef struct fsb_render_args {
  * Return a cudaError_t value (0 = success). *launches is incremented per kernel launch. */
 /* single != NULL: one pose whose constants travel as a kernel argument (and are stored to fc_dev[0]
  * by the kernel); otherwise fc_dev[n_poses] must already be in device memory. */
-int fsb_launch_setup(const fsb_frame_consts *fc_dev, const fsb_frame_consts *single, int n_poses, int max_nz,
-                     float *lines, float *invz, int zstride, void *stream, int64_t *launches);
+int fsb_launch_setup(const fsb_frame_consts *fc_dev, const fsb_frame_consts *single, int n_poses, float *table,
+                     int tab_stride, void *stream, int64_t *launches);
 int fsb_launch_march(const fsb_render_args *a, int use_packed, void *stream, int64_t *launches);
 int fsb_launch_expand(const fsb_render_args *a, void *stream, int64_t *launches);
 int fsb_launch_l2_stream(const uint32_t *buf, size_t n_words, uint32_t *sink, int blocks, void *stream);
