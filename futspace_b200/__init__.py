@@ -24,6 +24,7 @@ FILTER_NEAREST, FILTER_BILINEAR = 0, 1
 SENTINEL_ZERO, SENTINEL_SKY = 0, 1
 F2I_SATURATE, F2I_X86, F2I_MODERN = 0, 1, 2
 FLAG_FORCE_GENERIC = 1
+FLAG_NO_TEXTURE = 2
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_RANGE, ERR_NO_DEVICE = range(6)
 

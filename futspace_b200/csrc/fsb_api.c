@@ -46,6 +46,8 @@ struct fsb_context {
 };
 
 struct fsb_map {
+  cudaArray_t array;              /* RGBA8 copy of the packed texels for the texture path */
+  cudaTextureObject_t tex;
   uint32_t *packed, *color;
   int32_t *height;
   int q, r;
@@ -230,30 +232,61 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   m->pow2 = ((q & (q - 1)) == 0) && ((r & (r - 1)) == 0);
   while ((1 << m->log2r) < r) ++m->log2r;
   /* update_map, fut/interactive.fut:189: altitude = height & 0xFF */
-  /* the packed fast path needs power-of-two sizes holding at least one 8x4 tile (fsb_kernels.cu texel_x/texel_y) */
-  int packable = m->pow2 && r >= 8 && q >= 4;
+  /* packed texel = height byte + rgb + map-uniform alpha; the tiled __ldg layout also needs power-of-two
+   * sizes holding at least one 8x4 tile (fsb_kernels.cu texel_x/texel_y) */
+  int packable = 1;
+  const int tileable = m->pow2 && r >= 8 && q >= 4;
+  uint32_t *pk_rm = (uint32_t *)malloc(n * 4); /* row-major packed texels for the texture */
+  if (!pk_rm) {
+    free(m); free(hm); free(pk);
+    return set_err(ctx, FSB_ERR_NOMEM, "fsb_map_new: out of host memory");
+  }
   const uint32_t alpha = color[0] & 0xFF000000u;
   for (size_t i = 0; i < n; ++i) {
     int32_t hv = mask_heights ? (height[i] & 0xFF) : height[i];
     hm[i] = hv;
     if (hv < 0 || hv > 255 || (color[i] & 0xFF000000u) != alpha) packable = 0;
-    if (m->pow2 && r >= 8 && q >= 4) {
+    pk_rm[i] = ((uint32_t)hv << 24) | (color[i] & 0x00FFFFFFu);
+    if (tileable) {
       const size_t y = i / (size_t)r, x = i % (size_t)r;
       const size_t t = ((y >> 2) * (size_t)(r >> 3) + (x >> 3)) * 32 + ((y & 3) << 3) + (x & 7);
-      pk[t] = ((uint32_t)hv << 24) | (color[i] & 0x00FFFFFFu);
+      pk[t] = pk_rm[i];
     }
   }
   m->alpha_bits = alpha;
   cudaError_t e = cudaMalloc((void **)&m->color, n * 4);
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->height, n * 4);
-  if (e == cudaSuccess && packable) e = cudaMalloc((void **)&m->packed, n * 4);
+  if (e == cudaSuccess && packable && tileable) e = cudaMalloc((void **)&m->packed, n * 4);
+  if (e == cudaSuccess && packable && q <= 65536 && r <= 131072) {
+    struct cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
+    e = cudaMallocArray(&m->array, &cd, (size_t)r, (size_t)q, cudaArrayTextureGather);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DToArrayAsync(m->array, 0, 0, pk_rm, (size_t)r * 4, (size_t)r * 4, (size_t)q, cudaMemcpyHostToDevice,
+                                   ctx->stream);
+    if (e == cudaSuccess) {
+      struct cudaResourceDesc rd;
+      struct cudaTextureDesc td;
+      memset(&rd, 0, sizeof rd);
+      memset(&td, 0, sizeof td);
+      rd.resType = cudaResourceTypeArray;
+      rd.res.array.array = m->array;
+      td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap; /* floored modulo of the samplers */
+      td.filterMode = cudaFilterModePoint;
+      td.readMode = cudaReadModeElementType;
+      td.normalizedCoords = 1;
+      e = cudaCreateTextureObject(&m->tex, &rd, &td, NULL);
+    }
+  }
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->color, color, n * 4, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->height, hm, n * 4, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && packable) e = cudaMemcpyAsync(m->packed, pk, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && m->packed) e = cudaMemcpyAsync(m->packed, pk, n * 4, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   free(hm);
   free(pk);
+  free(pk_rm);
   if (e != cudaSuccess) {
+    if (m->tex) cudaDestroyTextureObject(m->tex);
+    if (m->array) cudaFreeArray(m->array);
     cudaFree(m->color); cudaFree(m->height); cudaFree(m->packed);
     free(m);
     return set_err(ctx, FSB_ERR_CUDA, "fsb_map_new: %s", cudaGetErrorString(e));
@@ -267,6 +300,8 @@ int fsb_map_free(fsb_context *ctx, fsb_map *m) {
   if (!m) return FSB_OK;
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (m->tex) cudaDestroyTextureObject(m->tex);
+  if (m->array) cudaFreeArray(m->array);
   cudaFree(m->color);
   cudaFree(m->height);
   cudaFree(m->packed);
@@ -274,7 +309,7 @@ int fsb_map_free(fsb_context *ctx, fsb_map *m) {
   return FSB_OK;
 }
 
-int fsb_map_is_packed(const fsb_map *m) { return m && m->packed != NULL; }
+int fsb_map_is_packed(const fsb_map *m) { return m && (m->packed != NULL || m->tex != 0); }
 
 /* ------------------------------------------------------------------------------------------ */
 static int ensure_tables(fsb_context *ctx, int n_poses, int tab_stride) {
@@ -393,7 +428,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   }
   int rc;
   if (n > 1) {
-    if ((rc = ensure_tables(ctx, n, 160))) return rc;
+    if ((rc = ensure_tables(ctx, n, 8 * 128))) return rc;
     CU(ctx, cudaEventSynchronize(ctx->fc_free));
     for (int i = 0; i < n; ++i) {
       if (make_consts(&cams[i], prm, w, &ctx->fc_host[i]))
@@ -402,8 +437,8 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
       if (ctx->fc_host[i].n_z > max_nz) max_nz = ctx->fc_host[i].n_z;
     }
   }
-  /* depth table: one 160-float block per chunk of 32 samples (fsb_kernels.cu FSB_TAB_BLOCK) */
-  const int tab_stride = 160 * (max_nz > 0 ? (max_nz + 31) / 32 : 1);
+  /* depth table: 8 floats per sample, padded by the 4 chunks the march loop prefetches past the end */
+  const int tab_stride = 8 * (32 * ((max_nz + 31) / 32) + 128);
   if ((rc = ensure_tables(ctx, n, tab_stride))) return rc;
   if ((rc = ensure_scratch(ctx, n, col_end - col_begin, h))) return rc;
   if (n > 1) {
@@ -448,9 +483,15 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.rec_cap = h;
   a.rb_shift = FSB_RB_SHIFT;
   a.n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
-  const int use_packed = map->packed && map->pow2 && prm->f2i_mode == FSB_F2I_SATURATE &&
-                         !(prm->flags & FSB_FLAG_FORCE_GENERIC);
-  CU(ctx, (cudaError_t)fsb_launch_march(&a, use_packed, ctx->stream, &ctx->launches));
+  a.tex = map->tex;
+  a.inv_r = 1.0f / (float)map->r;
+  a.inv_q = 1.0f / (float)map->q;
+  int mem = FSB_MEM_PLANES;
+  if (prm->f2i_mode == FSB_F2I_SATURATE && !(prm->flags & FSB_FLAG_FORCE_GENERIC)) {
+    if (map->tex && !(prm->flags & FSB_FLAG_NO_TEXTURE)) mem = FSB_MEM_TEX;
+    else if (map->packed) mem = FSB_MEM_TILED;
+  }
+  CU(ctx, (cudaError_t)fsb_launch_march(&a, mem, ctx->stream, &ctx->launches));
   if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
   CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));
   if (ctx->profiling) {

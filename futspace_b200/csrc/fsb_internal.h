@@ -30,12 +30,14 @@ typedef struct { uint32_t x, y; } uint2_fsb;
 typedef struct fsb_render_args {
   const uint32_t *packed;   /* height<<24 | rgb in 8x4-texel tiles (fsb_kernels.cu texel_x/texel_y), or NULL */
   int32_t xmask_hi, ymask_hi, log2r; /* tiled addressing: (r-1)&~7, (q-1)&~3, log2(r) */
+  unsigned long long tex;   /* cudaTextureObject_t over an RGBA8 array of the packed texels (bytes B,G,R,height), or 0 */
+  float inv_r, inv_q;       /* 1/r, 1/q for normalised texture coordinates */
   const uint32_t *color;    /* [q][r] argb  */
   const int32_t *height;    /* [q][r]       */
   int32_t q, r;
   const fsb_frame_consts *fc; /* device, [n_poses] */
-  const float *table;       /* device, [n_poses][tab_stride]: per chunk of 32 depth samples a 640-byte block */
-  int32_t tab_stride;       /* floats per pose = 160 * number of chunks                                      */
+  const float *table;       /* device, [n_poses][tab_stride]: 8 floats {sx,sy,dx,dy,inv_z,0,0,0} per depth sample */
+  int32_t tab_stride;       /* floats per pose = 8 * (32 * n_chunks + 128)                                      */
   uint32_t *out;            /* device; pixel (pose 0, row 0, column col_begin)              */
   int64_t row_stride;       /* pixels */
   int64_t pose_stride;      /* pixels */
@@ -57,7 +59,10 @@ typedef struct fsb_render_args {
  * by the kernel); otherwise fc_dev[n_poses] must already be in device memory. */
 int fsb_launch_setup(const fsb_frame_consts *fc_dev, const fsb_frame_consts *single, int n_poses, float *table,
                      int tab_stride, void *stream, int64_t *launches);
-int fsb_launch_march(const fsb_render_args *a, int use_packed, void *stream, int64_t *launches);
+#define FSB_MEM_PLANES 0
+#define FSB_MEM_TILED 1
+#define FSB_MEM_TEX 2
+int fsb_launch_march(const fsb_render_args *a, int mem, void *stream, int64_t *launches);
 int fsb_launch_expand(const fsb_render_args *a, void *stream, int64_t *launches);
 int fsb_launch_l2_stream(const uint32_t *buf, size_t n_words, uint32_t *sink, int blocks, void *stream);
 int fsb_launch_l2_gather(const uint32_t *buf, size_t n_sectors, uint32_t *sink, int blocks, int per_thread,

@@ -69,11 +69,12 @@ POSES = [
 
 @pytest.mark.parametrize("filt", [1, 0])
 @pytest.mark.parametrize("sentinel", [0, 1])
-def test_fbm_poses_packed(fsb, oracle, gpu_ctx, fbm1024, filt, sentinel):
+@pytest.mark.parametrize("flags", [0, 2], ids=["texture", "tiled_ldg"])
+def test_fbm_poses_packed(fsb, oracle, gpu_ctx, fbm1024, filt, sentinel, flags):
     col, hgt = fbm1024
     mp = gpu_ctx.upload_map(col, hgt)
     assert mp.packed
-    prm = fsb.default_params(filter=filt, sentinel=sentinel)
+    prm = fsb.default_params(filter=filt, sentinel=sentinel, flags=flags)
     for p in POSES:
         check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 768, 1024)
     mp.free()
@@ -112,6 +113,22 @@ def test_unpackable_maps(fsb, oracle, gpu_ctx):
     mp = gpu_ctx.upload_map(col, hgt, mask_heights=True)
     check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(150.3, 100.6, 300, 0.9, 150, 500, 1.2, SKY),
           fsb.default_params(), 240, 333, masked=True)
+    mp.free()
+
+
+@pytest.mark.parametrize("filt", [1, 0])
+def test_packed_texture_path_any_map_size(fsb, oracle, gpu_ctx, filt):
+    # packable content (heights <= 255, uniform alpha) on a non-power-of-two map: texture path with hardware wrap
+    rng = np.random.default_rng(11)
+    q, r = 300, 517
+    yy, xx = np.mgrid[0:q, 0:r]
+    hgt = (120 + 100 * np.sin(xx / 37.0) * np.cos(yy / 23.0)).astype(np.int32)
+    col = (rng.integers(0, 1 << 24, size=(q, r), dtype=np.uint64).astype(np.uint32)) | 0xFF000000
+    mp = gpu_ctx.upload_map(col, hgt)
+    assert mp.packed
+    prm = fsb.default_params(filter=filt)
+    for p in ((150.3, 100.6, 260, 0.9, 150, 500, 1.2), (-777.25, 5000.5, 230, 3.3, 100, 400, 1.0), (516.5, 299.5, 250, 5.0, 120, 300, 1.4)):
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 240, 333)
     mp.free()
 
 
