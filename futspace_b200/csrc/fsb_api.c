@@ -46,8 +46,8 @@ struct fsb_context {
 };
 
 struct fsb_map {
-  cudaArray_t array;              /* RGBA8 copy of the packed texels for the texture path */
-  cudaTextureObject_t tex;
+  cudaArray_t array, array_h;     /* RGBA8 packed texels / R16F heights for the texture path */
+  cudaTextureObject_t tex, tex_h;
   uint32_t *packed, *color;
   int32_t *height;
   int q, r;
@@ -211,6 +211,14 @@ int fsb_context_device_name(fsb_context *ctx, char *buf, size_t n) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* IEEE binary16 bits of an integer 0..255 (exact) */
+static uint16_t half_bits_of_byte(uint32_t v) {
+  if (v == 0) return 0;
+  int e = 0;
+  while ((v >> e) > 1) ++e;                       /* v = 1.m x 2^e, e <= 7 */
+  return (uint16_t)(((e + 15) << 10) | (((v << (10 - e)) & 0x3FF)));
+}
+
 int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, int q, int r, int mask_heights,
                 fsb_map **out) {
   if (!ctx) return FSB_ERR_ARG;
@@ -275,6 +283,21 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
       td.readMode = cudaReadModeElementType;
       td.normalizedCoords = 1;
       e = cudaCreateTextureObject(&m->tex, &rd, &td, NULL);
+      /* heights alone as IEEE half (0..255 are exact): the march gathers 2-byte texels and gets floats */
+      uint16_t *hh = (uint16_t *)malloc(n * 2);
+      if (!hh) e = cudaErrorMemoryAllocation;
+      if (e == cudaSuccess) {
+        for (size_t i = 0; i < n; ++i) hh[i] = half_bits_of_byte((uint32_t)hm[i]);
+        struct cudaChannelFormatDesc ch = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindFloat);
+        e = cudaMallocArray(&m->array_h, &ch, (size_t)r, (size_t)q, cudaArrayTextureGather);
+        if (e == cudaSuccess)
+          e = cudaMemcpy2DToArray(m->array_h, 0, 0, hh, (size_t)r * 2, (size_t)r * 2, (size_t)q, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+          rd.res.array.array = m->array_h;
+          e = cudaCreateTextureObject(&m->tex_h, &rd, &td, NULL);
+        }
+      }
+      free(hh);
     }
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->color, color, n * 4, cudaMemcpyHostToDevice, ctx->stream);
@@ -286,7 +309,9 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   free(pk_rm);
   if (e != cudaSuccess) {
     if (m->tex) cudaDestroyTextureObject(m->tex);
+    if (m->tex_h) cudaDestroyTextureObject(m->tex_h);
     if (m->array) cudaFreeArray(m->array);
+    if (m->array_h) cudaFreeArray(m->array_h);
     cudaFree(m->color); cudaFree(m->height); cudaFree(m->packed);
     free(m);
     return set_err(ctx, FSB_ERR_CUDA, "fsb_map_new: %s", cudaGetErrorString(e));
@@ -301,7 +326,9 @@ int fsb_map_free(fsb_context *ctx, fsb_map *m) {
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   if (m->tex) cudaDestroyTextureObject(m->tex);
+  if (m->tex_h) cudaDestroyTextureObject(m->tex_h);
   if (m->array) cudaFreeArray(m->array);
+  if (m->array_h) cudaFreeArray(m->array_h);
   cudaFree(m->color);
   cudaFree(m->height);
   cudaFree(m->packed);
@@ -428,7 +455,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   }
   int rc;
   if (n > 1) {
-    if ((rc = ensure_tables(ctx, n, 8 * 128))) return rc;
+    if ((rc = ensure_tables(ctx, n, 160 * 6))) return rc;
     CU(ctx, cudaEventSynchronize(ctx->fc_free));
     for (int i = 0; i < n; ++i) {
       if (make_consts(&cams[i], prm, w, &ctx->fc_host[i]))
@@ -437,8 +464,9 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
       if (ctx->fc_host[i].n_z > max_nz) max_nz = ctx->fc_host[i].n_z;
     }
   }
-  /* depth table: 8 floats per sample, padded by the 4 chunks the march loop prefetches past the end */
-  const int tab_stride = 8 * (32 * ((max_nz + 31) / 32) + 128);
+  /* depth table: one 160-float block per chunk of 32 samples, plus the blocks the march loop prefetches
+   * past the last chunk (fsb_kernels.cu) */
+  const int tab_stride = 160 * ((max_nz + 31) / 32 + 6);
   if ((rc = ensure_tables(ctx, n, tab_stride))) return rc;
   if ((rc = ensure_scratch(ctx, n, col_end - col_begin, h))) return rc;
   if (n > 1) {
@@ -484,11 +512,18 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.rb_shift = FSB_RB_SHIFT;
   a.n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
   a.tex = map->tex;
+  a.tex_h = map->tex_h;
   a.inv_r = 1.0f / (float)map->r;
   a.inv_q = 1.0f / (float)map->q;
   int mem = FSB_MEM_PLANES;
-  if (prm->f2i_mode == FSB_F2I_SATURATE && !(prm->flags & FSB_FLAG_FORCE_GENERIC)) {
-    if (map->tex && !(prm->flags & FSB_FLAG_NO_TEXTURE)) mem = FSB_MEM_TEX;
+  /* the fast paths take floor/ceil with a 2^23 rounding trick that needs |coordinate| < 2^22 */
+  int in_range = 1;
+  for (int i = 0; i < n; ++i) {
+    const double reach = (double)fabsf(cams[i].distance) * (1.0 + (double)fabsf(cams[i].fov)) * 1.01 + 4.0;
+    if (!((double)fabsf(cams[i].x) + reach < 4.0e6 && (double)fabsf(cams[i].y) + reach < 4.0e6)) in_range = 0;
+  }
+  if (in_range && prm->f2i_mode == FSB_F2I_SATURATE && !(prm->flags & FSB_FLAG_FORCE_GENERIC)) {
+    if (map->tex && map->tex_h && !(prm->flags & FSB_FLAG_NO_TEXTURE)) mem = FSB_MEM_TEX;
     else if (map->packed) mem = FSB_MEM_TILED;
   }
   CU(ctx, (cudaError_t)fsb_launch_march(&a, mem, ctx->stream, &ctx->launches));

@@ -31,13 +31,14 @@ typedef struct fsb_render_args {
   const uint32_t *packed;   /* height<<24 | rgb in 8x4-texel tiles (fsb_kernels.cu texel_x/texel_y), or NULL */
   int32_t xmask_hi, ymask_hi, log2r; /* tiled addressing: (r-1)&~7, (q-1)&~3, log2(r) */
   unsigned long long tex;   /* cudaTextureObject_t over an RGBA8 array of the packed texels (bytes B,G,R,height), or 0 */
+  unsigned long long tex_h; /* cudaTextureObject_t over an R16F array of the heights (exact for 0..255)                */
   float inv_r, inv_q;       /* 1/r, 1/q for normalised texture coordinates */
   const uint32_t *color;    /* [q][r] argb  */
   const int32_t *height;    /* [q][r]       */
   int32_t q, r;
   const fsb_frame_consts *fc; /* device, [n_poses] */
-  const float *table;       /* device, [n_poses][tab_stride]: 8 floats {sx,sy,dx,dy,inv_z,0,0,0} per depth sample */
-  int32_t tab_stride;       /* floats per pose = 8 * (32 * n_chunks + 128)                                      */
+  const float *table;       /* device, [n_poses][tab_stride]: per chunk of 32 depth samples a 640-byte block     */
+  int32_t tab_stride;       /* floats per pose = 160 * (n_chunks + 6): the march prefetches past the last chunk */
   uint32_t *out;            /* device; pixel (pose 0, row 0, column col_begin)              */
   int64_t row_stride;       /* pixels */
   int64_t pose_stride;      /* pixels */

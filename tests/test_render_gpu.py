@@ -64,6 +64,8 @@ POSES = [
     (-0.4, 0.3, 120, 0.3, 900, 500, 1.2),         # |coordinate| < 1: inexact bilinear weights; horizon > h
     (-2000.5, 77777.25, 200, 9.0, 384, 800, 2.0), # far outside the map: floored-modulo wrap
     (512.5, 512.5, 64, 1.0, 400, 400, 1.2),       # camera height == water level: NaN/inf at z = 0
+    (5.0e6, -7.25e6, 200, 0.5, 384, 300, 1.2),    # beyond the fast paths' coordinate range: generic kernel takes over
+    (4194000.5, 100.25, 200, 2.0, 384, 300, 1.2), # just inside / across the range bound
 ]
 
 
