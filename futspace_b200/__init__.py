@@ -85,6 +85,7 @@ SYMBOLS = {
     "fsb_copy_to_host": (_ci, [_vp, _vp, _vp, _sz]),
     "fsb_copy_to_device": (_ci, [_vp, _vp, _vp, _sz]),
     "fsb_terrain_fbm": (_ci, [_ci, ctypes.c_uint64, _vp, _vp]),
+    "fsb_selftest_sqrt": (_ci, [_vp, ctypes.c_uint32, ctypes.c_uint32, _P(ctypes.c_uint64)]),
     "fsb_bench_l2_stream": (_ci, [_vp, _sz, _ci, _P(ctypes.c_double)]),
     "fsb_bench_l2_gather": (_ci, [_vp, _sz, _ci, _P(ctypes.c_double)]),
 }
@@ -272,6 +273,11 @@ class Context:
         self.copy_to_host(out.ctypes.data, src_dev, out.nbytes)
         self.sync()
         return out
+
+    def selftest_sqrt(self, lo_bits, hi_bits):
+        v = ctypes.c_uint64()
+        self._check(lib().fsb_selftest_sqrt(self.handle, lo_bits, hi_bits, ctypes.byref(v)))
+        return v.value
 
     def l2_stream_gbs(self, nbytes=48 << 20, iters=20):
         v = ctypes.c_double()

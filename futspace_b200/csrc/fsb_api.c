@@ -654,6 +654,21 @@ int fsb_copy_to_device(fsb_context *ctx, void *dst, const void *src, size_t byte
 }
 
 /* ------------------------------------------------------------------------------------------ */
+int fsb_selftest_sqrt(fsb_context *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches) {
+  if (!ctx || !mismatches || lo_bits > hi_bits) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  unsigned long long *d = NULL, h = 0;
+  CU(ctx, cudaMalloc((void **)&d, 8));
+  CU(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
+  CU(ctx, (cudaError_t)fsb_launch_selftest_sqrt(lo_bits, hi_bits, d, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  *mismatches = h;
+  return FSB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 static int time_launches(fsb_context *ctx, int iters, int kind, const uint32_t *buf, size_t n, uint32_t *sink,
                          int per_thread, float *ms) {
   cudaEvent_t t0, t1;

@@ -33,6 +33,12 @@ def test_native_library_loaded(fsb, gpu_ctx):
     assert "libfutspace_b200.so" in maps
 
 
+def test_branch_free_sqrt_is_correctly_rounded(gpu_ctx):
+    # every float in [2^-100, 2.0) (bit patterns 0x0D800000 .. 0x40000000) and zero: identical to sqrt.rn.f32
+    assert gpu_ctx.selftest_sqrt(0x0D800000, 0x40000000) == 0
+    assert gpu_ctx.selftest_sqrt(0, 1) == 0
+
+
 def test_tests_variant_golden(fsb, oracle, gpu_ctx, c1w_d1, golden_frames):
     # tests/futspace.fut main: C1W/D1, fixed camera, 400x800 (colours without alpha -> packed path with alpha 0)
     rgb, hgt = c1w_d1
