@@ -361,7 +361,7 @@ static int ensure_tables(fsb_context *ctx, int n_poses, int tab_stride) {
 
 #define FSB_RB_SHIFT 8                   /* expand band = 256 rows */
 #define FSB_MAX_H 32768
-#define FSB_SCRATCH_BUDGET ((size_t)768 << 20)
+#define FSB_SCRATCH_BUDGET ((size_t)4096 << 20)
 
 static int ensure_scratch(fsb_context *ctx, int n_poses, int ncols, int h) {
   const int n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
@@ -387,6 +387,8 @@ static int ensure_scratch(fsb_context *ctx, int n_poses, int ncols, int h) {
 static int group_size(int n, int ncols, int h) {
   size_t per = (size_t)ncols * h * 8;
   size_t g = FSB_SCRATCH_BUDGET / (per ? per : 1);
+  const char *env = getenv("FSB_GROUP_POSES"); /* tuning aid: poses per launch group */
+  if (env && atoi(env) > 0) g = (size_t)atoi(env);
   if (g < 1) g = 1;
   if (g > FSB_MAX_POSES_PER_LAUNCH) g = FSB_MAX_POSES_PER_LAUNCH;
   return (size_t)n < g ? n : (int)g;
