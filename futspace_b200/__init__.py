@@ -73,6 +73,8 @@ SYMBOLS = {
     "fsb_map_new": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _P(_vp)]),
     "fsb_map_free": (_ci, [_vp, _vp]),
     "fsb_map_is_packed": (_ci, [_vp]),
+    "fsb_map_bake_shadows": (_ci, [_vp, _vp, _P(_cf), _ci, _ci, _vp]),
+    "fsb_sun_vector": (None, [_cf, _cf, _P(_cf)]),
     "fsb_render": (_ci, [_vp, _P(Camera), _P(Params), _vp, _ci, _ci, _vp]),
     "fsb_render_device": (_ci, [_vp, _P(Camera), _P(Params), _vp, _ci, _ci, _vp, ctypes.c_int64]),
     "fsb_render_batch_device": (_ci, [_vp, _P(Camera), _ci, _P(Params), _vp, _ci, _ci, _vp]),
@@ -129,6 +131,12 @@ def get_zs(delta, distance, z0, cap=1 << 22):
     buf = np.zeros(max(n, 1), np.float32)
     lib().fsb_get_zs(delta, distance, z0, buf.ctypes.data, min(n, cap))
     return buf[:n]
+
+
+def sun_vector(sun_height, sun_ang):
+    v = (_cf * 3)()
+    lib().fsb_sun_vector(sun_height, sun_ang, v)
+    return [v[0], v[1], v[2]]
 
 
 def terrain_fbm(m, seed=0x5EED5EED):
@@ -219,6 +227,14 @@ class Context:
         self._check(lib().fsb_map_new(self.handle, color.ctypes.data, height.ctypes.data, color.shape[0],
                                       color.shape[1], 1 if mask_heights else 0, ctypes.byref(h)))
         return Map(self, h, color.shape[0], color.shape[1])
+
+    def bake_shadows(self, mp, sun, out_q=None, out_r=None):
+        """fsb_map_bake_shadows -> shadowed colour map [out_q][out_r] (numpy u32)."""
+        out_q, out_r = out_q or mp.q, out_r or mp.r
+        out = np.empty((out_q, out_r), np.uint32)
+        s = (_cf * 3)(*sun)
+        self._check(lib().fsb_map_bake_shadows(self.handle, mp.handle, s, out_q, out_r, out.ctypes.data))
+        return out
 
     def render(self, cam, prm, mp, h, w, out=None):
         """fsb_render: host frame out (blocking)."""

@@ -336,6 +336,36 @@ int fsb_map_free(fsb_context *ctx, fsb_map *m) {
   return FSB_OK;
 }
 
+/* update_map's second half, fut/interactive.fut:194-196 -> fut/effects.fut:108-125 */
+int fsb_map_bake_shadows(fsb_context *ctx, const fsb_map *m, const float sun[3], int out_q, int out_r,
+                         uint32_t *out_host) {
+  if (!ctx) return FSB_ERR_ARG;
+  if (!m || !sun || !out_host || out_q <= 0 || out_r <= 0) return set_err(ctx, FSB_ERR_ARG, "fsb_map_bake_shadows: bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  uint32_t *d = NULL;
+  const size_t bytes = (size_t)out_q * out_r * 4;
+  CU(ctx, cudaMalloc((void **)&d, bytes));
+  cudaError_t e = (cudaError_t)fsb_launch_shadow(m->color, m->height, m->q, m->r, sun, out_q, out_r, d, ctx->stream,
+                                                 &ctx->launches);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return set_err(ctx, FSB_ERR_CUDA, "fsb_map_bake_shadows: %s", cudaGetErrorString(e));
+  return FSB_OK;
+}
+
+/* vec3_rotate #y sun_ang (vec3_rotate #z sun_height [0,1,0]), fut/effects.fut:6-25, fut/interactive.fut:56,196 */
+void fsb_sun_vector(float sun_height, float sun_ang, float out[3]) {
+  const float cz = cosf(sun_height), sz = sinf(sun_height), cy = cosf(sun_ang), sy = sinf(sun_ang);
+  /* R_z * [0,1,0]: rows summed left to right (linalg matvecmul_row) */
+  const float v0 = ((0.0f + cz * 0.0f) + (-sz) * 1.0f) + 0.0f * 0.0f;
+  const float v1 = ((0.0f + sz * 0.0f) + cz * 1.0f) + 0.0f * 0.0f;
+  const float v2 = ((0.0f + 0.0f * 0.0f) + 0.0f * 1.0f) + 1.0f * 0.0f;
+  out[0] = ((0.0f + cy * v0) + 0.0f * v1) + sy * v2;
+  out[1] = ((0.0f + 0.0f * v0) + 1.0f * v1) + 0.0f * v2;
+  out[2] = ((0.0f + (-sy) * v0) + 0.0f * v1) + cy * v2;
+}
+
 int fsb_map_is_packed(const fsb_map *m) { return m && (m->packed != NULL || m->tex != 0); }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -335,6 +335,64 @@ int fso_render_literal(const fso_camera *cam, const fso_params *prm, const uint3
   return 0;
 }
 
+/* fut/effects.fut:6-25 */
+static void rot(char axis, float ang, const float v[3], float o[3]) {
+  float c = cosf(ang), s = sinf(ang);
+  float R[3][3];
+  if (axis == 'x') {
+    float t[3][3] = {{1, 0, 0}, {0, c, -s}, {0, s, c}};
+    memcpy(R, t, sizeof R);
+  } else if (axis == 'y') {
+    float t[3][3] = {{c, 0, s}, {0, 1, 0}, {-s, 0, c}};
+    memcpy(R, t, sizeof R);
+  } else {
+    float t[3][3] = {{c, -s, 0}, {s, c, 0}, {0, 0, 1}};
+    memcpy(R, t, sizeof R);
+  }
+  for (int i = 0; i < 3; ++i) { /* matvecmul_row: reduce (+) 0 (map2 (*) row v) */
+    float a = R[i][0] * v[0], b = R[i][1] * v[1], d = R[i][2] * v[2];
+    float acc = 0.0f + a;
+    acc = acc + b;
+    o[i] = acc + d;
+  }
+}
+void fso_sun_vector(float sun_height, float sun_ang, float out[3]) {
+  const float sun0[3] = {0.0f, 1.0f, 0.0f}; /* fut/interactive.fut:56 */
+  float t[3];
+  rot('z', sun_height, sun0, t);
+  rot('y', sun_ang, t, out);
+}
+
+/* fut/effects.fut:108-125 */
+void fso_bake_shadows(const uint32_t *color, const int32_t *height, int q, int r, const float sun[3], int out_q,
+                      int out_r, uint32_t *out, int nthreads) {
+  const float step_size = (float)(1024 / 256); /* f32.i32 (max_dist / steps_per_ray), :109-111 */
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+  (void)nthreads;
+#endif
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (int y = 0; y < out_q; ++y)
+    for (int x = 0; x < out_r; ++x) {
+      float fx = (float)x, fy = (float)y;
+      float h0 = fso_height_nearest(height, q, r, fx, fy, FSO_F2I_SATURATE);
+      int count = 0;
+      for (int dist = 1; dist < 256; ++dist) { /* (1..<steps_per_ray), :118-121 */
+        float fd = (float)dist;
+        float t = fd * step_size;
+        float lift = t * sun[1];
+        float sx = t * sun[0], sy = t * sun[2];
+        float hh = fso_height_nearest(height, q, r, fx + sx, fy + sy, FSO_F2I_SATURATE);
+        float lhs = h0 + lift;
+        if (lhs - hh < -0.5f) ++count;
+      }
+      float amount = (float)count;
+      out[(size_t)y * out_r + x] =
+          fso_mix(step_size * amount, 0xFF000000u, 1.0f, fso_color_nearest(color, q, r, fx, fy, FSO_F2I_SATURATE)); /* :123 */
+    }
+}
+
 void fso_mask_heights(int32_t *hm, long n) { /* fut/interactive.fut:189 */
   for (long i = 0; i < n; ++i) hm[i] &= 0xFF;
 }

@@ -75,6 +75,16 @@ int fso_render(const fso_camera *cam, const fso_params *prm, const uint32_t *col
 int fso_render_literal(const fso_camera *cam, const fso_params *prm, const uint32_t *color,
                        const int32_t *height, int q, int r, int h, int w, uint32_t *out);
 
+/* generate_shadowmap_accumulated, fut/effects.fut:108-125, with the nearest samplers png_color / png_height
+ * as update_map passes them (fut/interactive.fut:194-196).  The reference hard-codes a 1024 x 1024 output
+ * (:124-125); `out_q x out_r` generalises that (pass 1024, 1024 for the reference behaviour).
+ * sun = vec3_rotate #y sun_ang (vec3_rotate #z sun_height [0,1,0]) -- see fso_sun_vector. */
+void fso_bake_shadows(const uint32_t *color, const int32_t *height, int q, int r, const float sun[3], int out_q,
+                      int out_r, uint32_t *out, int nthreads);
+/* fut/effects.fut:6-25 (vec3_rotate via linalg matvecmul_row, restated: row-major dot products summed left to
+ * right) applied as in fut/interactive.fut:196 to the initial sun [0,1,0] (:56). */
+void fso_sun_vector(float sun_height, float sun_ang, float out[3]);
+
 /* fut/interactive.fut:189 : height & 0xFF */
 void fso_mask_heights(int32_t *hm, long n);
 

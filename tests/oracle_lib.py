@@ -63,6 +63,8 @@ def lib():
         L.fso_render_literal.argtypes = [P(Camera), P(Params), vp, vp, ci, ci, ci, ci, vp]
         L.fso_render_literal.restype = ci
         L.fso_mask_heights.argtypes = [vp, ctypes.c_long]
+        L.fso_bake_shadows.argtypes = [vp, vp, ci, ci, P(cf), ci, ci, vp, ci]
+        L.fso_sun_vector.argtypes = [cf, cf, P(cf)]
         _lib = L
     return _lib
 
@@ -116,4 +118,20 @@ def render_literal(cam, prm, color, height, h, w):
                                   height.ctypes.data, color.shape[0], color.shape[1], h, w, out.ctypes.data)
     if rc:
         raise RuntimeError("fso_render_literal failed rc=%d" % rc)
+    return out
+
+
+def sun_vector(sun_height, sun_ang):
+    v = (ctypes.c_float * 3)()
+    lib().fso_sun_vector(sun_height, sun_ang, v)
+    return [v[0], v[1], v[2]]
+
+
+def bake_shadows(color, height, sun, out_q=None, out_r=None, nthreads=0):
+    color, height = _check_maps(color, height)
+    q, r = color.shape
+    out_q, out_r = out_q or q, out_r or r
+    out = np.empty((out_q, out_r), np.uint32)
+    s = (ctypes.c_float * 3)(*sun)
+    lib().fso_bake_shadows(color.ctypes.data, height.ctypes.data, q, r, s, out_q, out_r, out.ctypes.data, nthreads)
     return out

@@ -79,3 +79,11 @@ def test_no_cpu_fallback(fsb):
     with pytest.raises(fsb.FsbError) as e:
         fsb.Context(0)
     assert e.value.code == fsb.ERR_NO_DEVICE
+
+
+@pytest.mark.parametrize("sh,sa", [(0.1, 0.1), (1.3, 0.4), (-0.7, 2.9), (0.0, 0.0)])
+def test_sun_vector_matches_oracle(fsb, oracle, sh, sa):
+    # vec3_rotate #y sun_ang (vec3_rotate #z sun_height [0,1,0]), fut/interactive.fut:56,196
+    a, b = fsb.sun_vector(sh, sa), oracle.sun_vector(sh, sa)
+    assert np.array_equal(np.float32(a), np.float32(b))
+    assert abs(sum(x * x for x in a) - 1.0) < 1e-5

@@ -1,0 +1,113 @@
+"""The generated-API names (include/libfutspace.h): host-side state machine of fut/interactive.fut on CPU,
+and the full c/interactive.c call sequence on the GPU against the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import SKY
+import futhark_shim as FS
+
+f32 = np.float32
+
+
+@pytest.fixture()
+def session(fsb):
+    s = FS.Session()
+    s.error()          # on a box without a GPU the context carries an error; the state machine still works
+    s.init()
+    yield s
+    s.close()
+
+
+def test_init_state(session):
+    # fut/interactive.fut:29-36,54-55 via text_content (:185-186)
+    x, y, angle, height, horizon, distance, sun_h, sun_a, fov = session.text_content()
+    assert (f32(x), f32(y), height, f32(angle), horizon, distance, f32(fov)) == (f32(0.98), f32(0.6), 58.0, f32(2.2), 200.0, 800.0, f32(1.2))
+    assert (f32(sun_h), f32(sun_a)) == (f32(0.1), f32(0.1))
+
+
+def test_keys_and_step(session):
+    # process_inputs, fut/interactive.fut:89-125: every update reads the state before the step
+    session.key(True, ord("w"))
+    session.key(True, ord("a"))
+    session.key(True, ord("q"))
+    session.key(True, FS.SDLK_UP)
+    session.key(True, ord("o"))
+    session.step()
+    x, y, angle, height, horizon, distance, sun_h, sun_a, fov = session.text_content()
+    a0 = f32(2.2)
+    assert f32(x) == f32(f32(0.98) - f32(3) * f32(math.sin(a0))) or abs(x - (0.98 - 3 * math.sin(2.2))) < 1e-6
+    assert abs(y - (0.6 - 3 * math.cos(2.2))) < 1e-6
+    assert f32(angle) == f32(a0 + f32(0.10))
+    assert horizon == 220.0 and distance == 830.0
+    assert f32(fov) == f32(f32(1.2) + f32(0.1))
+    # keyup stops the motion; opposite keys
+    for k in (ord("w"), ord("a"), ord("q"), FS.SDLK_UP, ord("o")):
+        session.key(False, k)
+    before = session.text_content()
+    session.step()
+    assert session.text_content() == before
+    session.key(True, ord("s")); session.key(True, ord("d")); session.key(True, ord("e")); session.key(True, FS.SDLK_DOWN)
+    session.key(True, ord("l")); session.key(True, ord("r"))
+    session.step()
+    after = session.text_content()
+    assert f32(after[2]) == f32(f32(before[2]) - f32(0.10)) and after[4] == before[4] - 20 and after[5] == before[5] - 30
+    assert after[3] == before[3] + 10
+
+
+def test_terrain_collision_and_misc_events(session):
+    # no map yet: altitude is the dummy [[0],[0]] (fut/interactive.fut:38-43): height is clamped at 0
+    session.key(True, ord("f"))
+    for _ in range(8):
+        session.step()
+    assert session.text_content()[3] == 0.0      # 58 - 6*10 would be negative
+    session.mouse()
+    session.resize(480, 640)
+    assert session.text_content()[3] == 0.0
+
+
+def test_unknown_key_is_ignored(session):
+    before = session.text_content()
+    session.key(True, 0x7F)
+    session.step()
+    assert session.text_content() == before
+
+
+@pytest.mark.gpu
+def test_interactive_c_call_sequence_matches_oracle(fsb, oracle, c1w_d1):
+    rgb, hgt = c1w_d1
+    col = rgb | 0xFF000000                         # c/freeimage_futspace.h:52
+    raw_h = hgt | 0x00ABCD00                       # junk above bit 7: update_map masks with & 0xFF (fut/interactive.fut:189)
+    s = FS.Session()
+    assert s.error() is None
+    s.init()
+    s.update_map(col, raw_h)                       # load_map, c/interactive.c:25-57
+    s.resize(384, 512)
+    s.step()                                       # sets cam.sky_color = argb.scale 0xFF9090e0 sun_height (:163)
+    frame = s.render()
+    sun = oracle.sun_vector(0.1, 0.1)
+    shadowed = oracle.bake_shadows(col, hgt, sun, 1024, 1024)
+    sky = oracle.lib().fso_scale(0xFF9090E0, 0.1)
+    assert sky == 0x190E0E16
+    cam = oracle.Camera(0.98, 0.6, 58, 2.2, 200, 800, 1.2, sky)   # terrain under (0,0)... stays 58 unless higher
+    ground = float(hgt[0, 0])
+    cam.height = max(58.0, ground)
+    want = oracle.render(cam, oracle.default_params(), shadowed, hgt, 384, 512)
+    assert np.array_equal(frame, want)
+    # walk and turn for a few frames, raise the sun (re-bakes the shadows), compare again
+    s.key(True, ord("w")); s.key(True, ord("a")); s.key(True, ord("j"))
+    for _ in range(3):
+        s.step()
+    x, y, angle, height, horizon, distance, sun_h, sun_a, fov = s.text_content()
+    frame = s.render()
+    # the shadow map and sky in use come from the sun angles BEFORE the last step (fut/interactive.fut:126-136,163)
+    v2 = f32(f32(0.1) - f32(0.005)) - f32(0.005)
+    assert f32(sun_h) == f32(v2 - f32(0.005))
+    sun = oracle.sun_vector(float(v2), sun_a)
+    shadowed = oracle.bake_shadows(col, hgt, sun, 1024, 1024)
+    sky = oracle.lib().fso_scale(0xFF9090E0, float(v2))
+    cam = oracle.Camera(x, y, height, angle, horizon, distance, fov, sky)
+    want = oracle.render(cam, oracle.default_params(), shadowed, hgt, 384, 512)
+    assert np.array_equal(frame, want)
+    s.close()

@@ -246,3 +246,33 @@ def test_full_size_1080p_distance_2000(fsb, oracle, gpu_ctx):
     cam = fsb.Camera(m / 2 + 0.37, m / 2 + 0.73, 200, 2.2, 0.3 * 1080, 2000, 1.2, SKY)
     check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(), 1080, 1920)
     mp.free()
+
+
+@pytest.mark.parametrize("sun_height,sun_ang", [(0.1, 0.1), (1.3, 0.4), (1.45, -2.0)])
+def test_shadow_bake_matches_oracle(fsb, oracle, gpu_ctx, c1w_d1, sun_height, sun_ang):
+    # update_map's shadow bake (fut/interactive.fut:194-196, fut/effects.fut:108-125) on the reference's own map pair
+    rgb, hgt = c1w_d1
+    col = rgb | 0xFF000000
+    mp = gpu_ctx.upload_map(col, hgt)
+    sun = fsb.sun_vector(sun_height, sun_ang)
+    got = gpu_ctx.bake_shadows(mp, sun, 1024, 1024)
+    want = oracle.bake_shadows(col, hgt, sun, 1024, 1024)
+    assert np.array_equal(got, want)
+    if sun_height > 1.0:
+        assert (got != col).mean() > 0.05      # a low sun really casts shadows
+    mp.free()
+    # the baked map is what render draws (lsc.shadowed_color, fut/interactive.fut:181)
+    mp2 = gpu_ctx.upload_map(got, hgt)
+    cam = fsb.Camera(0.98, 0.6, 58, 2.2, 200, 800, 1.2, SKY)
+    check(fsb, oracle, gpu_ctx, mp2, got, hgt, cam, fsb.default_params(), 384, 512)
+    mp2.free()
+
+
+def test_shadow_bake_non_square_output(fsb, oracle, gpu_ctx, fbm1024):
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col[:300, :517].copy(), hgt[:300, :517].copy())
+    sun = fsb.sun_vector(1.2, 0.9)
+    got = gpu_ctx.bake_shadows(mp, sun, 200, 333)
+    want = oracle.bake_shadows(col[:300, :517].copy(), hgt[:300, :517].copy(), sun, 200, 333)
+    assert np.array_equal(got, want)
+    mp.free()
