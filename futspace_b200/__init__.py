@@ -86,6 +86,9 @@ SYMBOLS = {
     "fsb_host_free": (_ci, [_vp, _vp]),
     "fsb_copy_to_host": (_ci, [_vp, _vp, _vp, _sz]),
     "fsb_copy_to_device": (_ci, [_vp, _vp, _vp, _sz]),
+    "fsb_ipc_export": (_ci, [_vp, _vp, _vp]),
+    "fsb_ipc_import": (_ci, [_vp, _vp, _P(_vp)]),
+    "fsb_ipc_close": (_ci, [_vp, _vp]),
     "fsb_terrain_fbm": (_ci, [_ci, ctypes.c_uint64, _vp, _vp]),
     "fsb_selftest_sqrt": (_ci, [_vp, ctypes.c_uint32, ctypes.c_uint32, _P(ctypes.c_uint64)]),
     "fsb_bench_l2_stream": (_ci, [_vp, _sz, _ci, _P(ctypes.c_double)]),
@@ -294,6 +297,19 @@ class Context:
         v = ctypes.c_uint64()
         self._check(lib().fsb_selftest_sqrt(self.handle, lo_bits, hi_bits, ctypes.byref(v)))
         return v.value
+
+    def ipc_export(self, dev_ptr):
+        h = ctypes.create_string_buffer(64)
+        self._check(lib().fsb_ipc_export(self.handle, dev_ptr, h))
+        return h.raw
+
+    def ipc_import(self, handle_bytes):
+        p = _vp()
+        self._check(lib().fsb_ipc_import(self.handle, ctypes.create_string_buffer(handle_bytes, 64), ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, dev_ptr):
+        self._check(lib().fsb_ipc_close(self.handle, dev_ptr))
 
     def l2_stream_gbs(self, nbytes=48 << 20, iters=20):
         v = ctypes.c_double()

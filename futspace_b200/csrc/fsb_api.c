@@ -686,6 +686,30 @@ int fsb_copy_to_device(fsb_context *ctx, void *dst, const void *src, size_t byte
 }
 
 /* ------------------------------------------------------------------------------------------ */
+int fsb_ipc_export(fsb_context *ctx, void *dev_ptr, unsigned char handle[64]) {
+  if (!ctx || !dev_ptr || !handle) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CU(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle, &h, sizeof h);
+  return FSB_OK;
+}
+int fsb_ipc_import(fsb_context *ctx, const unsigned char handle[64], void **dev_ptr) {
+  if (!ctx || !dev_ptr || !handle) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  CU(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return FSB_OK;
+}
+int fsb_ipc_close(fsb_context *ctx, void *dev_ptr) {
+  if (!ctx || !dev_ptr) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaIpcCloseMemHandle(dev_ptr));
+  return FSB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 int fsb_selftest_sqrt(fsb_context *ctx, uint32_t lo_bits, uint32_t hi_bits, uint64_t *mismatches) {
   if (!ctx || !mismatches || lo_bits > hi_bits) return FSB_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->device));
