@@ -249,12 +249,29 @@ def run_ours(args, wl):
     value = total * args.steps / (total_ms / 1e3)
 
     # ---- per-kernel share + roofline of the dominant kernel (march) ----
+    # The roofline is taken with the occlusion bound switched off (FSB_FLAG_NO_CULL): every depth sample is
+    # fetched and evaluated, so the algorithmic bytes are really moved.  The default path (`value`) skips the
+    # chunks the bound proves hidden; its kernel times and the fraction of chunks it evaluates are reported too.
     ctx.set_profiling(True)
     step_dev()
     ctx.get_profile()
+    ctx.get_counters()
     for _ in range(2):
         step_dev()
+    prof_cull = ctx.get_profile()
+    chunks_eval, records = ctx.get_counters()
+    prm_full = F.default_params(flags=F.FLAG_NO_CULL)
+
+    def step_full():
+        ctx.render_batch_device(cam_arr, prm_full, mp, h, w, out_dev)
+
+    step_full()
+    ctx.get_profile()
+    ctx.get_counters()
+    for _ in range(2):
+        step_full()
     prof = ctx.get_profile()
+    chunks_full, _ = ctx.get_counters()
     ctx.set_profiling(False)
     march_ms, march_n = prof["march"]
     expand_ms, expand_n = prof["expand"]
@@ -269,10 +286,16 @@ def run_ours(args, wl):
                 "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": gather_bytes * poses_per_launch,
                 "launch_ms": march_ms / march_n,
-                "kernel_share_of_step": march_ms / (march_ms + expand_ms + setup_ms)}
+                "kernel_share_of_step": march_ms / (march_ms + expand_ms + setup_ms),
+                "mode": "occlusion bound off (FSB_FLAG_NO_CULL): all W*n_z samples evaluated",
+                "default_path": {"march_launch_ms": prof_cull["march"][0] / prof_cull["march"][1],
+                                 "chunks_evaluated_frac": chunks_eval / max(1, chunks_full),
+                                 "records_per_frame": records / (2.0 * P),
+                                 "kernel_ms_per_step": {k: v[0] / 2 for k, v in prof_cull.items()}}}
     step_alg = (gather_bytes + frame_alg) * P
-    roofline_step = {"achieved": step_alg / (total_ms / args.steps * 1e-3) / 1e9, "unit": "GB/s per GPU",
-                     "frac": step_alg / (total_ms / args.steps * 1e-3) / 1e9 / peak,
+    full_ms = (march_ms + expand_ms + setup_ms) / 2
+    roofline_step = {"achieved": step_alg / (full_ms * 1e-3) / 1e9, "unit": "GB/s per GPU (occlusion bound off)",
+                     "frac": step_alg / (full_ms * 1e-3) / 1e9 / peak,
                      "algorithmic_bytes_per_step_per_gpu": step_alg,
                      "kernel_ms_per_step": {"setup": setup_ms / 2, "march": march_ms / 2, "expand": expand_ms / 2}}
 
@@ -320,6 +343,7 @@ def run_ours(args, wl):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "frame": [w, h], "map": m, "distance": dst, "n_z": nz,
                    "filter": "bilinear", "poses_per_gpu_per_step": P, "global_poses_per_step": total,
+                   "occlusion_bound": "on (default path; frames bit-identical to the full evaluation, see roofline.default_path)",
                    "parallelism": "frame-parallel x%d, maps replicated, no collective" % world,
                    "l2": "256 MiB scratch write between timed steps (flush); each step also streams %.1f GB of "
                          "frames through the 126 MB L2; the %d MiB packed map is L2-resident by design"

@@ -25,6 +25,7 @@ SENTINEL_ZERO, SENTINEL_SKY = 0, 1
 F2I_SATURATE, F2I_X86, F2I_MODERN = 0, 1, 2
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_TEXTURE = 2
+FLAG_NO_CULL = 4
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_RANGE, ERR_NO_DEVICE = range(6)
 
@@ -67,6 +68,7 @@ SYMBOLS = {
     "fsb_context_device_name": (_ci, [_vp, ctypes.c_char_p, _sz]),
     "fsb_context_set_profiling": (_ci, [_vp, _ci]),
     "fsb_context_get_profile": (_ci, [_vp, _P(ctypes.c_double), _P(ctypes.c_int64)]),
+    "fsb_context_get_counters": (_ci, [_vp, _P(ctypes.c_uint64), _P(ctypes.c_uint64)]),
     "fsb_params_default": (None, [_P(Params)]),
     "fsb_params_tests_variant": (None, [_P(Params)]),
     "fsb_get_zs": (_ci, [_cf, _cf, _cf, _vp, _ci]),
@@ -220,6 +222,12 @@ class Context:
         n = (ctypes.c_int64 * 3)()
         self._check(lib().fsb_context_get_profile(self.handle, ms, n))
         return {k: (ms[i], n[i]) for i, k in enumerate(("setup", "march", "expand"))}
+
+    def get_counters(self):
+        """-> (chunks_evaluated, records) since the last call (profiling must be on)."""
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(lib().fsb_context_get_counters(self.handle, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def upload_map(self, color, height, mask_heights=True):
         color = np.ascontiguousarray(color, dtype=np.uint32)

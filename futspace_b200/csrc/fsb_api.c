@@ -39,6 +39,7 @@ struct fsb_context {
   double prof_ms[3];
   int64_t prof_n[3];
   int prof_pending;
+  unsigned long long *stats_dev;  /* profiling counters: chunks evaluated, records emitted */
   void *recs;                     /* march -> expand record lists */
   uint32_t *sidx;
   size_t recs_cap, sidx_cap;      /* bytes */
@@ -53,6 +54,7 @@ struct fsb_map {
   int q, r;
   int pow2, log2r;
   uint32_t alpha_bits;
+  float hmax;                     /* highest (masked) terrain height */
 };
 
 static int set_err(fsb_context *ctx, int code, const char *fmt, ...) {
@@ -116,7 +118,7 @@ int fsb_get_zs(float delta, float distance, float z0, float *out, int cap) {
   return n;
 }
 
-static int make_consts(const fsb_camera *cam, const fsb_params *prm, int w, fsb_frame_consts *fc) {
+static int make_consts(const fsb_camera *cam, const fsb_params *prm, const fsb_map *map, int w, fsb_frame_consts *fc) {
   float s = sinf(cam->angle), c = cosf(cam->angle), view = cam->fov;
   float sv = s * view, cv = c * view;
   fc->a_lx = -c - sv;
@@ -135,6 +137,11 @@ static int make_consts(const fsb_camera *cam, const fsb_params *prm, int w, fsb_
   fc->n_z = zs_length(prm->delta, cam->distance, prm->z0);
   fc->sky = cam->sky_color;
   fc->empty = prm->sentinel == FSB_SENTINEL_SKY ? cam->sky_color : 0u;
+  /* occlusion bound (fsb_kernels.cu): an interpolated height never exceeds the highest texel by 0.5 */
+  /* (only with the saturating conversion: the x86 / modern ones wrap huge rows to 0 and are not monotone) */
+  fc->cull_d = ((prm->flags & FSB_FLAG_NO_CULL) || prm->f2i_mode != FSB_F2I_SATURATE) ? -INFINITY
+                                                                                       : cam->height - (map->hmax + 0.5f);
+  fc->cull_lane = 0;
   return fc->n_z < 0 ? -1 : 0;
 }
 
@@ -181,6 +188,7 @@ void fsb_context_free(fsb_context *ctx) {
   cudaFree(ctx->frame_dev[1]);
   cudaFree(ctx->recs);
   cudaFree(ctx->sidx);
+  cudaFree(ctx->stats_dev);
   cudaEventDestroy(ctx->fc_free);
   for (int i = 0; i < 4; ++i)
     if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
@@ -253,6 +261,7 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   for (size_t i = 0; i < n; ++i) {
     int32_t hv = mask_heights ? (height[i] & 0xFF) : height[i];
     hm[i] = hv;
+    if (i == 0 || (float)hv > m->hmax) m->hmax = (float)hv;
     if (hv < 0 || hv > 255 || (color[i] & 0xFF000000u) != alpha) packable = 0;
     pk_rm[i] = ((uint32_t)hv << 24) | (color[i] & 0x00FFFFFFu);
     if (tileable) {
@@ -455,9 +464,26 @@ int fsb_context_set_profiling(fsb_context *ctx, int enable) {
   CU(ctx, cudaSetDevice(ctx->device));
   if (enable && !ctx->pev[0])
     for (int i = 0; i < 4; ++i) CU(ctx, cudaEventCreate(&ctx->pev[i]));
+  if (enable && !ctx->stats_dev) {
+    CU(ctx, cudaMalloc((void **)&ctx->stats_dev, 16));
+    CU(ctx, cudaMemsetAsync(ctx->stats_dev, 0, 16, ctx->stream));
+  }
   int rc = prof_collect(ctx);
   ctx->profiling = enable != 0;
   return rc;
+}
+
+int fsb_context_get_counters(fsb_context *ctx, uint64_t *chunks_evaluated, uint64_t *records) {
+  if (!ctx || !chunks_evaluated || !records) return FSB_ERR_ARG;
+  if (!ctx->stats_dev) return set_err(ctx, FSB_ERR_ARG, "fsb_context_get_counters: profiling was never enabled");
+  unsigned long long h[2] = {0, 0};
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync(h, ctx->stats_dev, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemsetAsync(ctx->stats_dev, 0, 16, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  *chunks_evaluated = h[0];
+  *records = h[1];
+  return FSB_OK;
 }
 
 int fsb_context_get_profile(fsb_context *ctx, double *ms, int64_t *launches) {
@@ -480,7 +506,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   fsb_frame_consts single;
   int max_nz = 0;
   if (n == 1) {
-    if (make_consts(&cams[0], prm, w, &single))
+    if (make_consts(&cams[0], prm, map, w, &single))
       return set_err(ctx, FSB_ERR_RANGE, "render: z-series undefined for distance=%g delta=%g z0=%g",
                      (double)cams[0].distance, (double)prm->delta, (double)prm->z0);
     max_nz = single.n_z;
@@ -490,7 +516,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if ((rc = ensure_tables(ctx, n, 160 * 6))) return rc;
     CU(ctx, cudaEventSynchronize(ctx->fc_free));
     for (int i = 0; i < n; ++i) {
-      if (make_consts(&cams[i], prm, w, &ctx->fc_host[i]))
+      if (make_consts(&cams[i], prm, map, w, &ctx->fc_host[i]))
         return set_err(ctx, FSB_ERR_RANGE, "render: z-series undefined for pose %d (distance=%g)", i,
                        (double)cams[i].distance);
       if (ctx->fc_host[i].n_z > max_nz) max_nz = ctx->fc_host[i].n_z;
@@ -538,6 +564,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.filter = prm->filter;
   a.f2i_mode = prm->f2i_mode;
   a.alpha_bits = map->alpha_bits;
+  a.stats = ctx->profiling ? ctx->stats_dev : NULL;
   a.recs = (uint2_fsb *)ctx->recs;
   a.sidx = ctx->sidx;
   a.rec_cap = h;

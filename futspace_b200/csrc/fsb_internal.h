@@ -19,6 +19,8 @@ typedef struct fsb_frame_consts {
   float z0, delta;
   int32_t n_z;
   uint32_t sky, empty;          /* empty = 0 (zero sentinel) or sky (sky sentinel) */
+  float cull_d;                 /* cam_h - (highest terrain + 0.5): no sample can project above this bound's row */
+  int32_t cull_lane;            /* lane of a 32-sample chunk whose inv_z minimises the bound (31 if cull_d >= 0 else 0) */
 } fsb_frame_consts;
 
 #ifdef __CUDACC__
@@ -52,6 +54,7 @@ typedef struct fsb_render_args {
   uint32_t *sidx;           /* [n_poses][ncols][n_bands+1]: sidx[b] = #records with row >= b<<rb_shift */
   int32_t rec_cap;          /* = h (rows strictly decrease along a list)                               */
   int32_t n_bands, rb_shift;
+  unsigned long long *stats; /* optional (profiling): [0] += chunks of 32 samples evaluated, [1] += records emitted */
 } fsb_render_args;
 
 /* launchers implemented in fsb_kernels.cu; stream is a cudaStream_t passed as void*.

@@ -77,7 +77,7 @@ POSES = [
 
 @pytest.mark.parametrize("filt", [1, 0])
 @pytest.mark.parametrize("sentinel", [0, 1])
-@pytest.mark.parametrize("flags", [0, 2], ids=["texture", "tiled_ldg"])
+@pytest.mark.parametrize("flags", [0, 2, 4], ids=["texture", "tiled_ldg", "texture_nocull"])
 def test_fbm_poses_packed(fsb, oracle, gpu_ctx, fbm1024, filt, sentinel, flags):
     col, hgt = fbm1024
     mp = gpu_ctx.upload_map(col, hgt)
