@@ -282,6 +282,7 @@ def run_ours(args, wl):
     peak, peak_src = measured_peaks()
     achieved = gather_bytes * poses_per_launch / (march_ms / march_n * 1e-3) / 1e9
     tr = ncu_traffic(args.workload)
+    tr = tr["dram_bytes_per_pose"] * poses_per_launch if tr else None
     roofline = {"bound": "hbm", "kernel": "fsb_march_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": gather_bytes * poses_per_launch,
@@ -509,7 +510,7 @@ def cpu_baseline(F, wl, col, hgt, total):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
