@@ -575,11 +575,15 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.inv_r = 1.0f / (float)map->r;
   a.inv_q = 1.0f / (float)map->q;
   int mem = FSB_MEM_PLANES;
-  /* the fast paths take floor/ceil with a 2^23 rounding trick that needs |coordinate| < 2^22 */
+  /* The texture path addresses texels with normalised coordinates (floor(x) + 1) / size and relies on that point
+   * staying within half a texel of the footprint centre.  For power-of-two sizes the division is exact; otherwise
+   * the two roundings cost up to 2^-23 * |coordinate| texels, so the coordinate range is kept where that is < 1/8.
+   * Beyond the range the generic kernel (integer addressing) renders the frame. */
+  const double limit = map->pow2 ? 4.0e6 : 1.0e6;
   int in_range = 1;
   for (int i = 0; i < n; ++i) {
     const double reach = (double)fabsf(cams[i].distance) * (1.0 + (double)fabsf(cams[i].fov)) * 1.01 + 4.0;
-    if (!((double)fabsf(cams[i].x) + reach < 4.0e6 && (double)fabsf(cams[i].y) + reach < 4.0e6)) in_range = 0;
+    if (!((double)fabsf(cams[i].x) + reach < limit && (double)fabsf(cams[i].y) + reach < limit)) in_range = 0;
   }
   if (in_range && prm->f2i_mode == FSB_F2I_SATURATE && !(prm->flags & FSB_FLAG_FORCE_GENERIC)) {
     if (map->tex && map->tex_h && !(prm->flags & FSB_FLAG_NO_TEXTURE)) mem = FSB_MEM_TEX;

@@ -135,7 +135,9 @@ def test_packed_texture_path_any_map_size(fsb, oracle, gpu_ctx, filt):
     mp = gpu_ctx.upload_map(col, hgt)
     assert mp.packed
     prm = fsb.default_params(filter=filt)
-    for p in ((150.3, 100.6, 260, 0.9, 150, 500, 1.2), (-777.25, 5000.5, 230, 3.3, 100, 400, 1.0), (516.5, 299.5, 250, 5.0, 120, 300, 1.4)):
+    for p in ((150.3, 100.6, 260, 0.9, 150, 500, 1.2), (-777.25, 5000.5, 230, 3.3, 100, 400, 1.0), (516.5, 299.5, 250, 5.0, 120, 300, 1.4),
+              (999000.25, -998500.5, 240, 1.1, 120, 300, 1.2),    # largest coordinates the texture path takes on a non-power-of-two map
+              (1.5e6, 2.5e6, 240, 1.1, 120, 300, 1.2)):           # beyond: generic kernel
         check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 240, 333)
     mp.free()
 
