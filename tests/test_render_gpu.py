@@ -278,3 +278,30 @@ def test_shadow_bake_non_square_output(fsb, oracle, gpu_ctx, fbm1024):
     want = oracle.bake_shadows(col[:300, :517].copy(), hgt[:300, :517].copy(), sun, 200, 333)
     assert np.array_equal(got, want)
     mp.free()
+
+
+def test_random_poses_fuzz(fsb, oracle, gpu_ctx, fbm1024, c1w_d1):
+    """Seeded fuzz over cameras, renderer constants, frame sizes and kernel variants; bit-exact or fail."""
+    rng = np.random.default_rng(20261017)
+    col, hgt = fbm1024
+    rgb, h2 = c1w_d1
+    maps = [(col, hgt, gpu_ctx.upload_map(col, hgt)), (rgb | 0xFF000000, h2, gpu_ctx.upload_map(rgb | 0xFF000000, h2))]
+    for it in range(48):
+        cmap, hmap, mp = maps[it % 2]
+        h, w = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        cam = fsb.Camera(float(rng.uniform(-3000, 3000)), float(rng.uniform(-3000, 3000)), float(rng.uniform(0, 400)),
+                         float(rng.uniform(-7, 7)), float(rng.uniform(-100, h + 100)), float(rng.uniform(0.5, 1500)),
+                         float(rng.uniform(0.3, 2.5)), int(rng.integers(0, 1 << 32)))
+        if it % 7 == 0:   # exact integers / half-integers provoke the degenerate weights (fact 9)
+            cam.x, cam.y, cam.angle = float(int(cam.x)), float(int(cam.y)) + 0.5, 0.0
+        prm = fsb.default_params() if it % 3 else fsb.tests_variant_params()
+        prm.filter = int(rng.integers(0, 2))
+        prm.sentinel = int(rng.integers(0, 2))
+        prm.flags = int(rng.choice([0, 0, 0, 1, 2, 4]))
+        if it % 5 == 0:
+            prm.invz_param1, prm.invz_param2 = float(rng.uniform(0.2, 3.0)), float(rng.uniform(20, 600))
+        if it % 11 == 0:
+            prm.z0, prm.delta = float(rng.uniform(0.0, 3.0)), float(rng.uniform(0.0005, 0.02))
+        check(fsb, oracle, gpu_ctx, mp, cmap, hmap, cam, prm, h, w)
+    for _, _, mp in maps:
+        mp.free()
