@@ -82,6 +82,8 @@ SYMBOLS = {
     "fsb_render_batch_device": (_ci, [_vp, _P(Camera), _ci, _P(Params), _vp, _ci, _ci, _vp]),
     "fsb_render_batch": (_ci, [_vp, _P(Camera), _ci, _P(Params), _vp, _ci, _ci, _vp]),
     "fsb_render_columns_device": (_ci, [_vp, _P(Camera), _P(Params), _vp, _ci, _ci, _ci, _ci, _vp, ctypes.c_int64]),
+    "fsb_effect_interpolate_device": (_ci, [_vp, _ci, _vp, _ci, _ci, _vp]),
+    "fsb_effect_interpolate2_device": (_ci, [_vp, _vp, _ci, _ci, _vp]),
     "fsb_device_malloc": (_ci, [_vp, _sz, _P(_vp)]),
     "fsb_device_free": (_ci, [_vp, _vp]),
     "fsb_host_malloc": (_ci, [_vp, _sz, _P(_vp)]),
@@ -275,6 +277,22 @@ class Context:
     def render_columns_device(self, cam, prm, mp, h, w, col_begin, col_end, out_dev, row_stride=0):
         self._check(lib().fsb_render_columns_device(self.handle, ctypes.byref(cam), ctypes.byref(prm), mp.handle,
                                                     h, w, col_begin, col_end, out_dev, row_stride))
+
+    def effect_interpolate(self, frame, pd=None):
+        """fut/effects.fut post-passes on a host frame: interpolate2 (pd None) or interpolate pd."""
+        frame = np.ascontiguousarray(frame, np.uint32)
+        h, w = frame.shape
+        a, b = self.device_malloc(frame.nbytes), self.device_malloc(frame.nbytes)
+        try:
+            self._check(lib().fsb_copy_to_device(self.handle, a, frame.ctypes.data, frame.nbytes))
+            if pd is None:
+                self._check(lib().fsb_effect_interpolate2_device(self.handle, a, h, w, b))
+            else:
+                self._check(lib().fsb_effect_interpolate_device(self.handle, pd, a, h, w, b))
+            return self.download(b, (h, w))
+        finally:
+            self.device_free(a)
+            self.device_free(b)
 
     def device_malloc(self, nbytes):
         p = _vp()

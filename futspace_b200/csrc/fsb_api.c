@@ -717,6 +717,23 @@ int fsb_copy_to_device(fsb_context *ctx, void *dst, const void *src, size_t byte
 }
 
 /* ------------------------------------------------------------------------------------------ */
+int fsb_effect_interpolate_device(fsb_context *ctx, int pd, const uint32_t *in_dev, int h, int w, uint32_t *out_dev) {
+  if (!ctx) return FSB_ERR_ARG;
+  if (!in_dev || !out_dev || in_dev == out_dev || h <= 0 || w <= 0) return set_err(ctx, FSB_ERR_ARG, "interpolate: bad argument");
+  if (h > w) return set_err(ctx, FSB_ERR_RANGE, "interpolate: needs h <= w (fut/effects.fut:36-41 wraps the x taps with %% h)");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, (cudaError_t)fsb_launch_interpolate(in_dev, h, w, 1, pd, out_dev, ctx->stream, &ctx->launches));
+  return FSB_OK;
+}
+int fsb_effect_interpolate2_device(fsb_context *ctx, const uint32_t *in_dev, int h, int w, uint32_t *out_dev) {
+  if (!ctx) return FSB_ERR_ARG;
+  if (!in_dev || !out_dev || in_dev == out_dev || h <= 0 || w <= 0) return set_err(ctx, FSB_ERR_ARG, "interpolate2: bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, (cudaError_t)fsb_launch_interpolate(in_dev, h, w, 0, 0, out_dev, ctx->stream, &ctx->launches));
+  return FSB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 int fsb_ipc_export(fsb_context *ctx, void *dev_ptr, unsigned char handle[64]) {
   if (!ctx || !dev_ptr || !handle) return FSB_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->device));

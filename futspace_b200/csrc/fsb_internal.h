@@ -70,6 +70,7 @@ int fsb_launch_march(const fsb_render_args *a, int mem, void *stream, int64_t *l
 int fsb_launch_expand(const fsb_render_args *a, void *stream, int64_t *launches);
 int fsb_launch_shadow(const uint32_t *color, const int32_t *height, int q, int r, const float *sun, int out_q, int out_r,
                       uint32_t *out, void *stream, int64_t *launches);
+int fsb_launch_interpolate(const uint32_t *img, int h, int w, int mode, int pd, uint32_t *out, void *stream, int64_t *launches);
 int fsb_launch_selftest_sqrt(uint32_t lo, uint32_t hi, unsigned long long *mismatches_dev, void *stream);
 int fsb_launch_l2_stream(const uint32_t *buf, size_t n_words, uint32_t *sink, int blocks, void *stream);
 int fsb_launch_l2_gather(const uint32_t *buf, size_t n_sectors, uint32_t *sink, int blocks, int per_thread,

@@ -393,6 +393,40 @@ void fso_bake_shadows(const uint32_t *color, const int32_t *height, int q, int r
     }
 }
 
+/* fut/effects.fut:27-45 */
+int fso_interpolate(int pd, const uint32_t *img, int h, int w, uint32_t *out) {
+  if (h > w) return 1; /* `(x +- pd) % h` (:36-41) would index past the row */
+#define PX(yy, xx) img[(size_t)(yy) * w + (xx)]
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int yu = floored_mod(y - pd, h), yd = floored_mod(y + pd, h);
+      int xl = floored_mod(x - pd, h), xr = floored_mod(x + pd, h); /* sic: % h */
+      uint32_t c = PX(y, x), u = PX(yu, x), d = PX(yd, x), l = PX(y, xl), r = PX(y, xr);
+      uint32_t ul = PX(yu, xl), ur = PX(yu, xr), dl = PX(yd, xl), dr = PX(yd, xr);
+      uint32_t acc = fso_mix(1.0f, dl, 1.0f, dr);
+      acc = fso_mix(1.0f, ur, 1.0f, acc);
+      acc = fso_mix(1.0f, ul, 1.0f, acc);
+      acc = fso_mix(1.0f, l, 1.0f, acc);
+      acc = fso_mix(1.0f, r, 1.0f, acc);
+      acc = fso_mix(1.0f, d, 1.0f, acc);
+      acc = fso_mix(1.0f, u, 1.0f, acc);
+      out[(size_t)y * w + x] = fso_mix(1.0f, c, 1.0f, acc);
+    }
+#undef PX
+  return 0;
+}
+/* fut/effects.fut:47-52: rotate (-1) xs puts xs[i-1] at i */
+void fso_interpolate2(const uint32_t *img, int h, int w, uint32_t *out) {
+  for (int y = 0; y < h; ++y) {
+    const uint32_t *mids = img + (size_t)y * w;
+    const uint32_t *highs = img + (size_t)floored_mod(y - 1, h) * w, *lows = img + (size_t)floored_mod(y + 1, h) * w;
+    for (int x = 0; x < w; ++x) {
+      uint32_t l = mids[floored_mod(x - 1, w)], c = mids[x], r = mids[floored_mod(x + 1, w)], u = highs[x], d = lows[x];
+      out[(size_t)y * w + x] = fso_mix(1.0f, l, 1.0f, fso_mix(1.0f, c, 1.0f, fso_mix(1.0f, r, 1.0f, fso_mix(1.0f, u, 1.0f, d))));
+    }
+  }
+}
+
 void fso_mask_heights(int32_t *hm, long n) { /* fut/interactive.fut:189 */
   for (long i = 0; i < n; ++i) hm[i] &= 0xFF;
 }

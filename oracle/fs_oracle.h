@@ -85,6 +85,12 @@ void fso_bake_shadows(const uint32_t *color, const int32_t *height, int q, int r
  * right) applied as in fut/interactive.fut:196 to the initial sun [0,1,0] (:56). */
 void fso_sun_vector(float sun_height, float sun_ang, float out[3]);
 
+/* Image-space post-passes of fut/effects.fut (never called by the reference; restated for completeness):
+ * interpolate pd (:27-45), 9 taps at distance pd nested in argb.mix 1 _ 1 _, x taps wrap with `% h` as written
+ * (:36-41; requires h <= w to stay in bounds); interpolate2 (:47-52), 5 taps via rotate. */
+int fso_interpolate(int pd, const uint32_t *img, int h, int w, uint32_t *out);
+void fso_interpolate2(const uint32_t *img, int h, int w, uint32_t *out);
+
 /* fut/interactive.fut:189 : height & 0xFF */
 void fso_mask_heights(int32_t *hm, long n);
 

@@ -65,6 +65,9 @@ def lib():
         L.fso_mask_heights.argtypes = [vp, ctypes.c_long]
         L.fso_bake_shadows.argtypes = [vp, vp, ci, ci, P(cf), ci, ci, vp, ci]
         L.fso_sun_vector.argtypes = [cf, cf, P(cf)]
+        L.fso_interpolate.argtypes = [ci, vp, ci, ci, vp]
+        L.fso_interpolate.restype = ci
+        L.fso_interpolate2.argtypes = [vp, ci, ci, vp]
         _lib = L
     return _lib
 
@@ -134,4 +137,19 @@ def bake_shadows(color, height, sun, out_q=None, out_r=None, nthreads=0):
     out = np.empty((out_q, out_r), np.uint32)
     s = (ctypes.c_float * 3)(*sun)
     lib().fso_bake_shadows(color.ctypes.data, height.ctypes.data, q, r, s, out_q, out_r, out.ctypes.data, nthreads)
+    return out
+
+
+def interpolate(pd, img):
+    img = np.ascontiguousarray(img, np.uint32)
+    out = np.empty_like(img)
+    if lib().fso_interpolate(pd, img.ctypes.data, img.shape[0], img.shape[1], out.ctypes.data):
+        raise ValueError("interpolate needs h <= w (fut/effects.fut:36-41 wraps x with % h)")
+    return out
+
+
+def interpolate2(img):
+    img = np.ascontiguousarray(img, np.uint32)
+    out = np.empty_like(img)
+    lib().fso_interpolate2(img.ctypes.data, img.shape[0], img.shape[1], out.ctypes.data)
     return out

@@ -141,3 +141,14 @@ def test_degenerate_sizes(oracle, fbm1024):
     assert len(oracle.get_zs(0.001, 0.002, 0.0)) == 2
     out = oracle.render(cam, oracle.default_params(), col, hgt, 1, 1)
     assert out.shape == (1, 1)
+
+
+def test_effects_post_passes_oracle(oracle):
+    img = np.full((6, 8), 0xFF808080, np.uint32)
+    assert np.array_equal(oracle.interpolate2(img), img)          # mixing equal colours is the identity
+    assert np.array_equal(oracle.interpolate(2, img), img)
+    img[2, 3] = 0xFFFFFFFF
+    out = oracle.interpolate2(img)
+    assert out[2, 3] != img[2, 3] and out[2, 2] != img[2, 2] and out[0, 0] == img[0, 0]
+    with pytest.raises(ValueError):
+        oracle.interpolate(1, np.zeros((8, 6), np.uint32))

@@ -305,3 +305,18 @@ def test_random_poses_fuzz(fsb, oracle, gpu_ctx, fbm1024, c1w_d1):
         check(fsb, oracle, gpu_ctx, mp, cmap, hmap, cam, prm, h, w)
     for _, _, mp in maps:
         mp.free()
+
+
+def test_effects_post_passes(fsb, oracle, gpu_ctx, fbm1024):
+    # fut/effects.fut:27-52 on a rendered frame (the reference never calls them; restated and matched anyway)
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    cam = fsb.Camera(512.37, 512.73, 180, 2.2, 90, 600, 1.2, SKY)
+    frame = gpu_ctx.render(cam, fsb.default_params(), mp, 200, 333)
+    assert np.array_equal(gpu_ctx.effect_interpolate(frame), oracle.interpolate2(frame))
+    for pd in (1, 3):
+        assert np.array_equal(gpu_ctx.effect_interpolate(frame, pd), oracle.interpolate(pd, frame))
+    with pytest.raises(fsb.FsbError) as e:      # h > w: the reference's `% h` on x would read out of bounds
+        gpu_ctx.effect_interpolate(frame[:, :100].copy(), 1)
+    assert e.value.code == fsb.ERR_RANGE
+    mp.free()
