@@ -320,3 +320,23 @@ def test_effects_post_passes(fsb, oracle, gpu_ctx, fbm1024):
         gpu_ctx.effect_interpolate(frame[:, :100].copy(), 1)
     assert e.value.code == fsb.ERR_RANGE
     mp.free()
+
+
+def test_full_size_8k_in_column_slabs(fsb, oracle, gpu_ctx):
+    # BASELINE config 5 frame (7680x4320, distance 4000) assembled from 4 column slabs written into one frame;
+    # the map is 4096^2 here (the 16384^2 one is exercised by bench.py --workload 8k-colsplit)
+    from futspace_b200.shard import column_bounds
+    col, hgt = fsb.terrain_fbm(4096)
+    mp = gpu_ctx.upload_map(col, hgt)
+    h, w = 4320, 7680
+    cam = fsb.Camera(2048.37, 2048.73, 210, 2.2, 0.3 * h, 4000, 1.2, SKY)
+    prm = fsb.default_params()
+    dev = gpu_ctx.device_malloc(h * w * 4)
+    b = column_bounds(w, 4)
+    for r in range(4):
+        gpu_ctx.render_columns_device(cam, prm, mp, h, w, b[r], b[r + 1], dev + 4 * b[r], w)
+    got = gpu_ctx.download(dev, (h, w))
+    want = oracle.render(ocam(oracle, cam), oprm(oracle, prm), col, hgt, h, w)
+    assert np.array_equal(got, want)
+    gpu_ctx.device_free(dev)
+    mp.free()
