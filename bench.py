@@ -43,10 +43,11 @@ WORKLOADS = {
 }
 
 
-def camera_path(F_or_O, height_map, m, n_total, first, count, h, dist):
-    """SURVEY.md 8d path; camera height clamped to terrain + 20 as terrain_collision would (fut/interactive.fut:67-87)."""
+def camera_path(F_or_O, height_map, m, n_total, first, count, h, dist, stride=1):
+    """SURVEY.md 8d path; camera height clamped to terrain + 20 as terrain_collision would (fut/interactive.fut:67-87).
+    Poses first, first + stride, ... (count of them) of an n_total-pose loop."""
     cams = []
-    for i in range(first, first + count):
+    for i in range(first, first + count * stride, stride):
         th = 2.0 * math.pi * i / n_total
         x = m / 2 + (m / 4) * math.cos(th)
         y = m / 2 + (m / 4) * math.sin(th)
@@ -223,7 +224,7 @@ def run_ours(args, wl):
     prm = F.default_params()
     nz = n_z_of(F, prm, dst)
     total = P * world
-    cams = camera_path(F, hgt, m, total, rank * P, P, h, dst)
+    cams = camera_path(F, hgt, m, total, rank, P, h, dst, stride=world)   # pose i -> rank i mod N (shard.pose_interleave)
     cam_arr = (F.Camera * P)(*cams)
     frame_bytes = w * h * 4
     st = torch.cuda.ExternalStream(ctx.stream)
@@ -345,7 +346,7 @@ def run_ours(args, wl):
         "config": {"workload": wl["name"], "frame": [w, h], "map": m, "distance": dst, "n_z": nz,
                    "filter": "bilinear", "poses_per_gpu_per_step": P, "global_poses_per_step": total,
                    "occlusion_bound": "on (default path; frames bit-identical to the full evaluation, see roofline.default_path)",
-                   "parallelism": "frame-parallel x%d, maps replicated, no collective" % world,
+                   "parallelism": "frame-parallel x%d (pose i -> GPU i mod N), maps replicated, no collective" % world,
                    "l2": "256 MiB scratch write between timed steps (flush); each step also streams %.1f GB of "
                          "frames through the 126 MB L2; the %d MiB packed map is L2-resident by design"
                          % (P * frame_bytes / 1e9, m * m * 4 >> 20)},

@@ -15,6 +15,12 @@ def pose_shard(n_total, rank, world):
     return first, base + (1 if rank < rem else 0)
 
 
+def pose_interleave(n_total, rank, world):
+    """-> list of pose indices for `rank` under round-robin sharding (pose i -> rank i mod world).  Every rank's poses
+    span the whole camera path, so the per-GPU work of a weak-scaling run does not depend on the rank."""
+    return list(range(rank, n_total, world))
+
+
 def column_bounds(w, world, align=32):
     """-> world+1 boundaries: slab r is [b[r], b[r+1]); interior boundaries are multiples of `align`."""
     units = (w + align - 1) // align

@@ -26,6 +26,15 @@ def test_pose_shard_partitions_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_pose_interleave_partitions_everything():
+    from futspace_b200.shard import pose_interleave
+    for n in (1, 7, 512, 2048):
+        for world in (1, 2, 4, 8):
+            seen = sorted(i for r in range(world) for i in pose_interleave(n, r, world))
+            assert seen == list(range(n))
+    assert pose_interleave(8, 1, 4) == [1, 5]
+
+
 def test_column_bounds_aligned_and_complete():
     from futspace_b200.shard import column_bounds
     for w in (1, 31, 32, 1000, 1920, 3840, 7680):
