@@ -340,3 +340,16 @@ def test_full_size_8k_in_column_slabs(fsb, oracle, gpu_ctx):
     assert np.array_equal(got, want)
     gpu_ctx.device_free(dev)
     mp.free()
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 1), (3, 5), (4, 8), (7, 64)])
+def test_tiny_maps(fsb, oracle, gpu_ctx, shape):
+    # down to the reference's dummy landscape [[0],[0]] (fut/interactive.fut:38-43): everything wraps
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    hgt = rng.integers(0, 256, size=shape).astype(np.int32)
+    col = rng.integers(0, 1 << 24, size=shape, dtype=np.uint64).astype(np.uint32) | 0xFF000000
+    mp = gpu_ctx.upload_map(col, hgt)
+    for filt in (0, 1):
+        for cam in (fsb.Camera(0.98, 0.6, 300, 2.2, 40, 200, 1.2, SKY), fsb.Camera(-3.5, 2.25, 120, 0.4, 60, 150, 0.9, SKY)):
+            check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(filter=filt), 96, 128)
+    mp.free()
