@@ -113,6 +113,23 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Run this rank on the CPUs NVML reports as local to its GPU, so the pinned frame buffers of the e2e leg are
+    first-touched on the GPU's own NUMA node (matters when several ranks stream frames to the host at once)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -198,6 +215,7 @@ def run_ours(args, wl):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d (one process per GPU)" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
+    pin_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
