@@ -398,7 +398,7 @@ static int ensure_tables(fsb_context *ctx, int n_poses, int tab_stride) {
   return FSB_OK;
 }
 
-#define FSB_RB_SHIFT 8                   /* expand band = 256 rows */
+#define FSB_RB_SHIFT 5                   /* band of the per-column record index = 32 rows (fsb_expand_kernel) */
 #define FSB_MAX_H 32768
 #define FSB_SCRATCH_BUDGET ((size_t)4096 << 20)
 
