@@ -54,7 +54,7 @@ struct fsb_map {
   int q, r;
   int pow2, log2r;
   uint32_t alpha_bits;
-  float hmax;                     /* highest (masked) terrain height */
+  int32_t hmax;                   /* highest (masked) terrain height */
 };
 
 static int set_err(fsb_context *ctx, int code, const char *fmt, ...) {
@@ -137,10 +137,13 @@ static int make_consts(const fsb_camera *cam, const fsb_params *prm, const fsb_m
   fc->n_z = zs_length(prm->delta, cam->distance, prm->z0);
   fc->sky = cam->sky_color;
   fc->empty = prm->sentinel == FSB_SENTINEL_SKY ? cam->sky_color : 0u;
-  /* occlusion bound (fsb_kernels.cu): an interpolated height never exceeds the highest texel by 0.5 */
+  /* occlusion bound (fsb_kernels.cu): an interpolated height never exceeds the highest texel by more than the
+   * rounding of its seven f32 operations -- 0.5 plus a relative 2e-6 covers any i32 height; rounded upward */
+  const double hb = (double)map->hmax + 0.5 + fabs((double)map->hmax) * 2.0e-6;
+  const float hbound = nextafterf((float)hb, INFINITY);
   /* (only with the saturating conversion: the x86 / modern ones wrap huge rows to 0 and are not monotone) */
   fc->cull_d = ((prm->flags & FSB_FLAG_NO_CULL) || prm->f2i_mode != FSB_F2I_SATURATE) ? -INFINITY
-                                                                                       : cam->height - (map->hmax + 0.5f);
+                                                                                       : cam->height - hbound;
   fc->cull_lane = 0;
   return fc->n_z < 0 ? -1 : 0;
 }
@@ -261,7 +264,7 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   for (size_t i = 0; i < n; ++i) {
     int32_t hv = mask_heights ? (height[i] & 0xFF) : height[i];
     hm[i] = hv;
-    if (i == 0 || (float)hv > m->hmax) m->hmax = (float)hv;
+    if (i == 0 || hv > m->hmax) m->hmax = hv;
     if (hv < 0 || hv > 255 || (color[i] & 0xFF000000u) != alpha) packable = 0;
     pk_rm[i] = ((uint32_t)hv << 24) | (color[i] & 0x00FFFFFFu);
     if (tileable) {

@@ -353,3 +353,24 @@ def test_tiny_maps(fsb, oracle, gpu_ctx, shape):
         for cam in (fsb.Camera(0.98, 0.6, 300, 2.2, 40, 200, 1.2, SKY), fsb.Camera(-3.5, 2.25, 120, 0.4, 60, 150, 0.9, SKY)):
             check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(filter=filt), 96, 128)
     mp.free()
+
+
+def test_huge_unmasked_heights(fsb, oracle, gpu_ctx):
+    # i32 heights around +-1e9 (two-plane generic kernel, occlusion bound active): f32 rounding of the interpolation is
+    # tens of units here, the bound's margin must cover it
+    rng = np.random.default_rng(5)
+    q, r = 256, 256
+    yy, xx = np.mgrid[0:q, 0:r]
+    hgt = (1.0e9 * np.sin(xx / 17.0) * np.cos(yy / 29.0)).astype(np.int32)
+    col = rng.integers(0, 1 << 24, size=(q, r), dtype=np.uint64).astype(np.uint32) | 0xFF000000
+    mp = gpu_ctx.upload_map(col, hgt, mask_heights=False)
+    assert not mp.packed
+    for cam_h in (9.99e8, 1.2e9, -3.0e8):
+        for filt in (0, 1):
+            prm = fsb.default_params(filter=filt, invz_param1=2.0e-7)
+            cam = fsb.Camera(100.3, 77.7, cam_h, 0.9, 120, 400, 1.2, SKY)
+            a = check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, 240, 200, masked=False)
+            prm.flags = fsb.FLAG_NO_CULL
+            b = gpu_ctx.render(cam, prm, mp, 240, 200)
+            assert np.array_equal(a, b)
+    mp.free()
