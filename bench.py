@@ -62,7 +62,8 @@ def n_z_of(F, prm, dist):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock, power and throttle reasons sampled every 20 ms through NVML while the timed region runs
+    (falls back to an `nvidia-smi -lms 100` subprocess when pynvml is not importable)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -71,8 +72,22 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []
+        self.stop_flag = False
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -82,11 +97,39 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            n = self.nvml
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm = sorted(x[0] for x in self.samples)
+            reasons = sorted(k for k, b in bits.items() if any(x[2] & b for x in self.samples))
+            return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.smax),
+                    "power_w_max": max((x[1] for x in self.samples), default=None), "samples": len(sm),
+                    "reasons": reasons, "source": "nvml, 20 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -110,7 +153,8 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 100"}
 
 
 def pin_to_gpu_numa_node(gpu_index):
