@@ -14,7 +14,20 @@
 #include "../../include/libfutspace.h"
 
 struct futhark_context_config { int device; };
-struct futhark_context { fsb_context *fsb; char *error; };
+#define POOL_SLOTS 4
+struct futhark_context {
+  fsb_context *fsb;
+  char *error;
+  /* frames are returned to a small pool instead of cudaFree (which synchronises the device): the lys loop
+   * allocates and frees one frame per displayed image */
+  struct { void *dev; size_t bytes; } pool[POOL_SLOTS];
+  /* futhark_values_u32_2d of a device frame: asynchronous copy into pinned staging, delivered to the caller's
+   * (pageable) buffer by futhark_context_sync -- the generated API's contract is "valid after sync" */
+  void *staging;
+  size_t staging_bytes;
+  uint32_t *pending_dst;
+  size_t pending_bytes;
+};
 struct futhark_u32_2d { int64_t shape[2]; uint32_t *host; uint32_t *dev; };
 struct futhark_i32_2d { int64_t shape[2]; int32_t *host; };
 
@@ -70,15 +83,50 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg) 
   }
   return ctx;
 }
+static void *pool_get(struct futhark_context *ctx, size_t bytes) {
+  for (int i = 0; i < POOL_SLOTS; ++i)
+    if (ctx->pool[i].dev && ctx->pool[i].bytes == bytes) {
+      void *p = ctx->pool[i].dev;
+      ctx->pool[i].dev = NULL;
+      return p;
+    }
+  void *p = NULL;
+  return fsb_device_malloc(ctx->fsb, bytes, &p) ? NULL : p;
+}
+static void pool_put(struct futhark_context *ctx, void *dev, size_t bytes) {
+  for (int i = 0; i < POOL_SLOTS; ++i)
+    if (!ctx->pool[i].dev) {
+      ctx->pool[i].dev = dev;
+      ctx->pool[i].bytes = bytes;
+      return;
+    }
+  fsb_device_free(ctx->fsb, dev);
+}
+static int flush_pending(struct futhark_context *ctx) { /* after a stream sync: staging -> caller's buffer */
+  if (ctx->pending_dst) {
+    memcpy(ctx->pending_dst, ctx->staging, ctx->pending_bytes);
+    ctx->pending_dst = NULL;
+  }
+  return 0;
+}
+
 void futhark_context_free(struct futhark_context *ctx) {
   if (!ctx) return;
+  if (ctx->fsb) {
+    fsb_context_sync(ctx->fsb);
+    flush_pending(ctx);
+    for (int i = 0; i < POOL_SLOTS; ++i)
+      if (ctx->pool[i].dev) fsb_device_free(ctx->fsb, ctx->pool[i].dev);
+    if (ctx->staging) fsb_host_free(ctx->fsb, ctx->staging);
+  }
   fsb_context_free(ctx->fsb);
   free(ctx->error);
   free(ctx);
 }
 int futhark_context_sync(struct futhark_context *ctx) {
   if (!ctx || !ctx->fsb) return fail(ctx, "no device context");
-  return fsb_context_sync(ctx->fsb) ? fail_fsb(ctx) : 0;
+  if (fsb_context_sync(ctx->fsb)) return fail_fsb(ctx);
+  return flush_pending(ctx);
 }
 char *futhark_context_get_error(struct futhark_context *ctx) {
   if (!ctx) return NULL;
@@ -101,7 +149,7 @@ struct futhark_u32_2d *futhark_new_u32_2d(struct futhark_context *ctx, const uin
 }
 int futhark_free_u32_2d(struct futhark_context *ctx, struct futhark_u32_2d *a) {
   if (!a) return 0;
-  if (a->dev && ctx && ctx->fsb) fsb_device_free(ctx->fsb, a->dev);
+  if (a->dev && ctx && ctx->fsb) pool_put(ctx, a->dev, (size_t)a->shape[0] * a->shape[1] * 4);
   free(a->host);
   free(a);
   return 0;
@@ -111,7 +159,21 @@ int futhark_values_u32_2d(struct futhark_context *ctx, struct futhark_u32_2d *a,
   const size_t bytes = (size_t)a->shape[0] * a->shape[1] * 4;
   if (a->host) { memcpy(data, a->host, bytes); return 0; }
   if (!ctx || !ctx->fsb) return fail(ctx, "no device context");
-  return fsb_copy_to_host(ctx->fsb, data, a->dev, bytes) ? fail_fsb(ctx) : 0; /* asynchronous until futhark_context_sync */
+  if (ctx->pending_dst) { /* an earlier values() not yet synced: deliver it first */
+    if (fsb_context_sync(ctx->fsb)) return fail_fsb(ctx);
+    flush_pending(ctx);
+  }
+  if (bytes > ctx->staging_bytes) {
+    if (ctx->staging) fsb_host_free(ctx->fsb, ctx->staging);
+    ctx->staging = NULL;
+    ctx->staging_bytes = 0;
+    if (fsb_host_malloc(ctx->fsb, bytes, &ctx->staging)) return fail_fsb(ctx);
+    ctx->staging_bytes = bytes;
+  }
+  if (fsb_copy_to_host(ctx->fsb, ctx->staging, a->dev, bytes)) return fail_fsb(ctx); /* asynchronous until futhark_context_sync */
+  ctx->pending_dst = data;
+  ctx->pending_bytes = bytes;
+  return 0;
 }
 const int64_t *futhark_shape_u32_2d(struct futhark_context *ctx, struct futhark_u32_2d *a) { (void)ctx; return a ? a->shape : NULL; }
 
@@ -356,8 +418,8 @@ int futhark_entry_render(struct futhark_context *ctx, struct futhark_u32_2d **ou
   struct futhark_u32_2d *a = (struct futhark_u32_2d *)calloc(1, sizeof *a);
   if (!a) return fail(ctx, "out of memory");
   a->shape[0] = s->height; a->shape[1] = s->width;
-  void *dev = NULL;
-  if (fsb_device_malloc(ctx->fsb, (size_t)s->height * s->width * 4, &dev)) { free(a); return fail_fsb(ctx); }
+  void *dev = pool_get(ctx, (size_t)s->height * s->width * 4);
+  if (!dev) { free(a); return fail_fsb(ctx); }
   a->dev = (uint32_t *)dev;
   fsb_params prm;
   fsb_params_default(&prm); /* #png, #off: fut/interactive.fut:179-183 */
