@@ -26,6 +26,7 @@ F2I_SATURATE, F2I_X86, F2I_MODERN = 0, 1, 2
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_TEXTURE = 2
 FLAG_NO_CULL = 4
+FLAG_SMOOTHING = 8
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_RANGE, ERR_NO_DEVICE = range(6)
 

@@ -407,7 +407,7 @@ static int ensure_tables(fsb_context *ctx, int n_poses, int tab_stride) {
 
 static int ensure_scratch(fsb_context *ctx, int n_poses, int ncols, int h) {
   const int n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
-  const size_t need_r = (size_t)n_poses * ncols * h * 8, need_s = (size_t)n_poses * ncols * (n_bands + 1) * 4;
+  const size_t need_r = (size_t)n_poses * ncols * (h + 1) * 8, need_s = (size_t)n_poses * ncols * (n_bands + 1) * 4;
   if (need_r > ctx->recs_cap) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->recs);
@@ -427,7 +427,7 @@ static int ensure_scratch(fsb_context *ctx, int n_poses, int ncols, int h) {
 
 /* poses per launch group: bounded by the record-list scratch budget */
 static int group_size(int n, int ncols, int h) {
-  size_t per = (size_t)ncols * h * 8;
+  size_t per = (size_t)ncols * (h + 1) * 8;
   size_t g = FSB_SCRATCH_BUDGET / (per ? per : 1);
   const char *env = getenv("FSB_GROUP_POSES"); /* tuning aid: poses per launch group */
   if (env && atoi(env) > 0) g = (size_t)atoi(env);
@@ -508,6 +508,8 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
                         int64_t pose_stride) {
   fsb_frame_consts single;
   int max_nz = 0;
+  if (row_stride > (int64_t)(INT32_MAX / 4)) /* fsb_expand_kernel forms row offsets from a 32-bit byte stride */
+    return set_err(ctx, FSB_ERR_ARG, "render: row_stride %lld too large", (long long)row_stride);
   if (n == 1) {
     if (make_consts(&cams[0], prm, map, w, &single))
       return set_err(ctx, FSB_ERR_RANGE, "render: z-series undefined for distance=%g delta=%g z0=%g",
@@ -524,6 +526,12 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
                        (double)cams[i].distance);
       if (ctx->fc_host[i].n_z > max_nz) max_nz = ctx->fc_host[i].n_z;
     }
+  }
+  if (prm->flags & FSB_FLAG_SMOOTHING) {
+    if (prm->sentinel != FSB_SENTINEL_ZERO)
+      return set_err(ctx, FSB_ERR_ARG, "render: smoothing exists only with the zero sentinel (fut/voxel_renderer.fut:175-213)");
+    if (max_nz > (1 << 17)) /* the record word holds row (15 bits) | sample index (17 bits) */
+      return set_err(ctx, FSB_ERR_RANGE, "render: smoothing supports at most %d depth samples, got %d", 1 << 17, max_nz);
   }
   /* depth table: one 160-float block per chunk of 32 samples, plus the blocks the march loop prefetches
    * past the last chunk (fsb_kernels.cu) */
@@ -570,8 +578,9 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.stats = ctx->profiling ? ctx->stats_dev : NULL;
   a.recs = (uint2_fsb *)ctx->recs;
   a.sidx = ctx->sidx;
-  a.rec_cap = h;
+  a.rec_cap = h + 1; /* + the guard record */
   a.rb_shift = FSB_RB_SHIFT;
+  a.smooth = (prm->flags & FSB_FLAG_SMOOTHING) ? 1 : 0;
   a.n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
   a.tex = map->tex;
   a.tex_h = map->tex_h;

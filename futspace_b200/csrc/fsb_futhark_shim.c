@@ -422,7 +422,8 @@ int futhark_entry_render(struct futhark_context *ctx, struct futhark_u32_2d **ou
   if (!dev) { free(a); return fail_fsb(ctx); }
   a->dev = (uint32_t *)dev;
   fsb_params prm;
-  fsb_params_default(&prm); /* #png, #off: fut/interactive.fut:179-183 */
+  fsb_params_default(&prm); /* #png: fut/interactive.fut:179-183 */
+  if (s->smoothing_on) prm.flags |= FSB_FLAG_SMOOTHING; /* s.smoothing_mode, :182 (key `2`, :153-159) */
   if (fsb_render_device(ctx->fsb, &s->cam, &prm, s->lsc->shadowed, s->height, s->width, a->dev, 0)) {
     futhark_free_u32_2d(ctx, a);
     return fail_fsb(ctx);

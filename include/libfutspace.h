@@ -8,9 +8,10 @@
  * consumed; futhark_context_get_error returns a malloc'ed string (or NULL) that the caller frees.
  *
  * The nine entry points are those of fut/interactive_entrypoints.fut:6-32; the state machine behind them
- * follows fut/interactive.fut:28-198 and fut/interactive_input.fut.  Not implemented (out of the hot-path
- * scope): the #math render mode (key `1` toggles the flag, rendering stays #png) and the
- * smoothing variant (key `2`, fut/voxel_renderer.fut:175-213).
+ * follows fut/interactive.fut:28-198 and fut/interactive_input.fut.  Key `2` toggles the smoothing
+ * variant (fut/voxel_renderer.fut:175-213, rendered with FSB_FLAG_SMOOTHING: see futspace_b200.h for the semantics
+ * adopted where the reference is unspecified).  Not implemented (out of the hot-path scope): the #math
+ * render mode (key `1` toggles the flag, rendering stays #png).
  */
 #ifndef LIBFUTSPACE_H
 #define LIBFUTSPACE_H

@@ -146,7 +146,7 @@ void fso_params_default(fso_params *p) {
   p->filter = FSO_FILTER_BILINEAR;  /* fut/interactive.fut:180-181 */
   p->sentinel = FSO_SENTINEL_ZERO;  /* fut/voxel_renderer.fut:244-248 */
   p->f2i_mode = FSO_F2I_SATURATE;   /* default backend opencl, Makefile:4 */
-  p->reserved = 0;
+  p->smoothing = 0;
 }
 void fso_params_tests_variant(fso_params *p) {
   p->z0 = 1.0f;            /* tests/futspace.fut:84 */
@@ -156,7 +156,7 @@ void fso_params_tests_variant(fso_params *p) {
   p->filter = FSO_FILTER_NEAREST;   /* :76-79, :95-96 */
   p->sentinel = FSO_SENTINEL_SKY;   /* :110-121 */
   p->f2i_mode = FSO_F2I_SATURATE;
-  p->reserved = 0;
+  p->smoothing = 0;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -240,6 +240,74 @@ static int check_args(const fso_camera *cam, const fso_params *prm, const void *
                       int r, int h, int w, const void *out) {
   if (!cam || !prm || !a || !b || !out) return 1;
   if (q <= 0 || r <= 0 || h <= 0 || w <= 0) return 2;
+  if (prm->smoothing && prm->sentinel != FSO_SENTINEL_ZERO) return 2; /* #on exists only in fut/voxel_renderer.fut */
+  return 0;
+}
+
+/* The pixel of row `row` inside the span of a smoothing tuple (col, prev col, y, prev y, idx, prev idx),
+ * fut/voxel_renderer.fut:200-210. */
+static inline uint32_t smooth_pixel(uint32_t c, uint32_t cprev, int32_t y, int32_t yprev, int32_t k, int32_t kprev,
+                                    int32_t row) {
+  if (k - kprev != 1) return c;
+  const float range = fmaxf(1.0f, (float)(yprev - y));
+  const float delta1 = fabsf((float)row - (float)yprev) / range;
+  const float delta2 = fabsf((float)y - (float)row) / range;
+  return fso_mix(delta2, cprev, delta1, c);
+}
+
+/* Smoothing #on, sequential statement (see fs_oracle.h): per column the list of samples that lower the y-buffer,
+ * then rows top-down. */
+static int render_smooth(const fso_camera *cam, const fso_params *prm, const uint32_t *color, const int32_t *height,
+                         int q, int r, int h, int w, uint32_t *out, int eval_all, int nthreads, const depth_line *L,
+                         int n) {
+  const int bil = prm->filter == FSO_FILTER_BILINEAR, m = prm->f2i_mode;
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+  (void)nthreads;
+#endif
+#pragma omp parallel num_threads(nthreads)
+  {
+    int32_t *rk = (int32_t *)malloc(sizeof(int32_t) * (size_t)(h + 1));
+    int32_t *ry = (int32_t *)malloc(sizeof(int32_t) * (size_t)(h + 1));
+    uint32_t *rcol = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(h + 1));
+#pragma omp for schedule(dynamic, 4)
+    for (int j = 0; j < w; ++j) {
+      int cnt = 0;
+      int32_t ybuf = h;
+      for (int k = 0; k < n; ++k) {
+        float x, y;
+        seg_point(&L[k], j, &x, &y);
+        float hgt = bil ? fso_height_bilinear(height, q, r, x, y, m) : fso_height_nearest(height, q, r, x, y, m);
+        uint32_t c = 0;
+        if (eval_all) c = bil ? fso_color_bilinear(color, q, r, x, y, m) : fso_color_nearest(color, q, r, x, y, m);
+        int32_t yy = project(cam, prm, &L[k], hgt);
+        if (yy < ybuf) { /* occlude2 :87-90 keeps the earlier sample on ties */
+          if (!eval_all) c = bil ? fso_color_bilinear(color, q, r, x, y, m) : fso_color_nearest(color, q, r, x, y, m);
+          rk[cnt] = k; ry[cnt] = yy; rcol[cnt] = c;
+          ++cnt;
+          ybuf = yy;
+        }
+      }
+      /* rows above the last record stay at the sentinel tuple: colour 0 -> sky */
+      int row = 0;
+      const int top = cnt ? ry[cnt - 1] : h;
+      for (; row < top; ++row) out[(size_t)row * w + j] = cam->sky_color;
+      for (int i = cnt - 1; i >= 0; --i) {
+        /* previous running-minimum state: record i-1 or the neutral element (0, h, 0) of :188 */
+        const uint32_t cprev = i ? rcol[i - 1] : 0u;
+        const int32_t yprev = i ? ry[i - 1] : h, kprev = i ? rk[i - 1] : 0;
+        /* the lowering tuple survives the scatter only if no later sample rewrites the row */
+        const int keep = (i + 1 < cnt && rk[i + 1] == rk[i] + 1) || rk[i] == n - 1;
+        const int end = yprev < h ? yprev : h;
+        for (; row < end; ++row) {
+          uint32_t px = keep ? smooth_pixel(rcol[i], cprev, ry[i], yprev, rk[i], kprev, row) : rcol[i];
+          out[(size_t)row * w + j] = px == 0u ? cam->sky_color : px;
+        }
+      }
+    }
+    free(rk); free(ry); free(rcol);
+  }
   return 0;
 }
 
@@ -257,6 +325,11 @@ int fso_render(const fso_camera *cam, const fso_params *prm, const uint32_t *col
 #else
   (void)nthreads;
 #endif
+  if (prm->smoothing) {
+    rc = render_smooth(cam, prm, color, height, q, r, h, w, out, eval_all, nthreads, L, n);
+    free(L);
+    return rc;
+  }
 #pragma omp parallel num_threads(nthreads)
   {
     uint32_t *col = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)h);
@@ -313,6 +386,38 @@ int fso_render_literal(const fso_camera *cam, const fso_params *prm, const uint3
       cs[(size_t)k * w + i] = c;
       hs[(size_t)k * w + i] = project(cam, prm, &L[k], hgt);
     }
+  if (prm->smoothing) {
+    /* rendered_image2, :186-212, with `futhark c` semantics for the unspecified parts (see fs_oracle.h) */
+    typedef struct { uint32_t c, cp; int32_t y, yp, k, kp; } tup;
+    const tup sentinel = {0u, 0u, 0, 0, 1000, 1000};
+    uint32_t *sc = (uint32_t *)malloc((size_t)(n > 0 ? n : 1) * 4);
+    int32_t *sy = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * 4), *sk = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * 4);
+    tup *line = (tup *)malloc((size_t)h * sizeof(tup));
+    if (!sc || !sy || !sk || !line) { free(sc); free(sy); free(sk); free(line); free(cs); free(hs); free(col); free(L); return 3; }
+    for (int j = 0; j < w; ++j) {
+      uint32_t ac = 0; int32_t ah = h, ak = 0; /* scan occlude2 (0, h, 0), :188 */
+      for (int k = 0; k < n; ++k) {
+        const uint32_t c2 = cs[(size_t)k * w + j]; const int32_t h2 = hs[(size_t)k * w + j];
+        if (!(ah <= h2)) { ac = c2; ah = h2; ak = k; }
+        sc[k] = ac; sy[k] = ah; sk[k] = ak;
+      }
+      for (int i = 0; i < h; ++i) line[i] = sentinel; /* replicate h (0,0,0,0,1000,1000), :192 */
+      for (int k = 0; k < n; ++k) {                   /* rotate (-1): element k pairs with element k-1, wrapping */
+        const int p = k ? k - 1 : n - 1;
+        const tup t = {sc[k], sc[p], sy[k], sy[p], sk[k], sk[p]};
+        if (sy[k] >= 0 && sy[k] < h) line[sy[k]] = t;   /* scatter in index order: the last write wins */
+      }
+      tup acc = sentinel; /* scan fill_vline3, :193 */
+      for (int i = 0; i < h; ++i) {
+        const tup t = line[i];
+        if (!(t.c == 0u && t.cp == 0u && t.y == 0 && t.yp == 0 && t.k == 1000 && t.kp == 1000)) acc = t;
+        const uint32_t px = smooth_pixel(acc.c, acc.cp, acc.y, acc.yp, acc.k, acc.kp, i);
+        out[(size_t)i * w + j] = px == 0u ? cam->sky_color : px; /* :211 */
+      }
+    }
+    free(sc); free(sy); free(sk); free(line); free(cs); free(hs); free(col); free(L);
+    return 0;
+  }
   /* rendered_image, :229-250, over (transpose height_color_map) */
   for (int j = 0; j < w; ++j) {
     /* scan occlude (0,h) : inclusive; res[0] = xs[0] */

@@ -41,7 +41,7 @@ typedef struct {
   int32_t filter;    /* png_*_filtered (1, fut/interactive.fut:180-181) or png_* (0)         */
   int32_t sentinel;  /* 0: colour 0 is "empty" (voxel_renderer.fut:244-248) ; 1: sky (voxel_renderer_new.fut:182-194) */
   int32_t f2i_mode;
-  int32_t reserved;
+  int32_t smoothing; /* 0: #off (fut/voxel_renderer.fut:214-251) ; 1: #on (:175-213), see fso_render */
 } fso_params;
 
 void fso_params_default(fso_params *p);       /* live renderer constants */
@@ -59,6 +59,16 @@ float fso_height_nearest(const int32_t *hm, int q, int r, float x, float y, int 
 float fso_height_bilinear(const int32_t *hm, int q, int r, float x, float y, int f2i_mode);
 uint32_t fso_color_nearest(const uint32_t *cm, int q, int r, float x, float y, int f2i_mode);
 uint32_t fso_color_bilinear(const uint32_t *cm, int q, int r, float x, float y, int f2i_mode);
+
+/* Smoothing #on (fut/voxel_renderer.fut:175-213) scatters DIFFERENT tuples to the same row: the sample that lowers
+ * the running minimum writes (colour, previous colour, row, previous row, idx, previous idx) and every later sample
+ * that keeps that minimum rewrites the row with (colour, colour, row, row, idx, idx) (:196-198).  Futhark leaves the
+ * winner unspecified; the oracle (and the CUDA path) take the semantics of the sequential `futhark c` backend that
+ * BASELINE config 1 names: scans fold left to right starting from the neutral element, scatter writes in index order
+ * (the last write wins).  Net effect: the span of sample k is blended towards the previous visible colour
+ * (argb.mix by row distance, :204-210) exactly when samples k-1, k and k+1 all lower the y-buffer (or k is the last
+ * sample); colour 0 is not transparent in this mode (fill_vline3 only skips the (0,0,0,0,1000,1000) sentinel).
+ * Requires the zero sentinel. */
 
 /* Sequential front-to-back march per column (SURVEY.md 8a "equivalent sequential statement").
  * eval_all_colors != 0 evaluates the colour sampler for every sample as the reference does

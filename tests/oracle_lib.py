@@ -26,7 +26,7 @@ class Camera(ctypes.Structure):
 
 class Params(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in "z0 delta invz_param1 invz_param2".split()] + [
-        (n, ctypes.c_int32) for n in "filter sentinel f2i_mode reserved".split()]
+        (n, ctypes.c_int32) for n in "filter sentinel f2i_mode smoothing".split()]
 
 
 def build(force=False):

@@ -110,4 +110,17 @@ def test_interactive_c_call_sequence_matches_oracle(fsb, oracle, c1w_d1):
     cam = oracle.Camera(x, y, height, angle, horizon, distance, fov, sky)
     want = oracle.render(cam, oracle.default_params(), shadowed, hgt, 384, 512)
     assert np.array_equal(frame, want)
+    # key `2` toggles smoothing (fut/interactive.fut:153-159) on the step after the key-down event
+    s.key(False, ord("w")); s.key(False, ord("a")); s.key(False, ord("j"))
+    s.key(True, ord("2"))
+    s.step()
+    s.key(False, ord("2"))
+    s.step()
+    x, y, angle, height, horizon, distance, sun_h2, sun_a2, fov = s.text_content()
+    assert (sun_h2, sun_a2) == (sun_h, sun_a)      # no sun key held: the shadow map baked above stays in use
+    cam = oracle.Camera(x, y, height, angle, horizon, distance, fov, oracle.lib().fso_scale(0xFF9090E0, sun_h))
+    frame = s.render()
+    want = oracle.render(cam, oracle.default_params(smoothing=1), shadowed, hgt, 384, 512)
+    assert np.array_equal(frame, want)
+    assert not np.array_equal(frame, oracle.render(cam, oracle.default_params(), shadowed, hgt, 384, 512))
     s.close()

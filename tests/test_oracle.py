@@ -152,3 +152,27 @@ def test_effects_post_passes_oracle(oracle):
     assert out[2, 3] != img[2, 3] and out[2, 2] != img[2, 2] and out[0, 0] == img[0, 0]
     with pytest.raises(ValueError):
         oracle.interpolate(1, np.zeros((8, 6), np.uint32))
+
+
+def test_smoothing_on_two_formulations_agree(oracle, c1w_d1):
+    """Smoothing #on (fut/voxel_renderer.fut:175-213): the sequential statement (list of lowering samples, spans
+    blended when three consecutive samples lower the y-buffer) against the reference pipeline taken literally
+    (scan occlude2 / rotate / scatter in index order / scan fill_vline3 / map), and against #off."""
+    rgb, hgt = c1w_d1
+    col = rgb | np.uint32(0xFF000000)
+    changed = 0
+    for cam in (oracle.Camera(512.3, 800.7, 78, 0.3, 100, 300, 1.0, SKY), oracle.Camera(300.5, 200.25, 120, 2.2, 60, 500, 1.2, SKY),
+                oracle.Camera(100.0, 7.0, 30, -0.7, 150, 400, 0.8, SKY)):
+        for filt in (0, 1):
+            on = oracle.default_params(smoothing=1, filter=filt)
+            a = oracle.render(cam, on, col, hgt, 160, 200)
+            b = oracle.render_literal(cam, on, col, hgt, 160, 200)
+            assert np.array_equal(a, b)
+            off = oracle.render(cam, oracle.default_params(filter=filt), col, hgt, 160, 200)
+            assert (a != off).mean() < 0.5
+            changed += int((a != off).any())
+            if filt == 0:   # nearest C1W colours are never 0: same silhouette
+                assert np.array_equal(a == SKY, off == SKY)
+    assert changed >= 4
+    with pytest.raises(RuntimeError):   # no smoothing in the sky-sentinel renderer (fut/voxel_renderer_new.fut)
+        oracle.render(cam, oracle.default_params(smoothing=1, sentinel=1), col, hgt, 16, 16)

@@ -15,7 +15,8 @@ def ocam(oracle, cam):
 
 
 def oprm(oracle, p):
-    return oracle.Params(p.z0, p.delta, p.invz_param1, p.invz_param2, p.filter, p.sentinel, p.f2i_mode, 0)
+    return oracle.Params(p.z0, p.delta, p.invz_param1, p.invz_param2, p.filter, p.sentinel, p.f2i_mode,
+                         1 if p.flags & 8 else 0)  # FSB_FLAG_SMOOTHING -> fso_params.smoothing
 
 
 def check(fsb, oracle, ctx, mp, color, height, cam, prm, h, w, masked=True):
@@ -373,4 +374,43 @@ def test_huge_unmasked_heights(fsb, oracle, gpu_ctx):
             prm.flags = fsb.FLAG_NO_CULL
             b = gpu_ctx.render(cam, prm, mp, 240, 200)
             assert np.array_equal(a, b)
+    mp.free()
+
+
+@pytest.mark.parametrize("filt", [1, 0])
+@pytest.mark.parametrize("flags", [8, 8 | 1, 8 | 2, 8 | 4], ids=["texture", "generic", "tiled_ldg", "texture_nocull"])
+def test_smoothing_on(fsb, oracle, gpu_ctx, fbm1024, c1w_d1, filt, flags):
+    """Smoothing #on (fut/voxel_renderer.fut:175-213) under the sequential-scatter semantics the oracle states."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    prm = fsb.default_params(filter=filt, flags=flags)
+    for p in POSES[:6]:
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 300, 400)
+    # ragged sizes: partial bands, a single column, a single row
+    for h, w in ((1, 1), (33, 5), (95, 64), (257, 31)):
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*POSES[0][:4], 0.3 * h, 500, 1.2, SKY), prm, h, w)
+    mp.free()
+    rgb, h2 = c1w_d1
+    mp = gpu_ctx.upload_map(rgb | 0xFF000000, h2)
+    cam = fsb.Camera(0.98, 0.6, 58, 2.2, 200, 1000, 1.2, SKY)   # the demo's initial pose, fut/interactive.fut:28-36
+    on = check(fsb, oracle, gpu_ctx, mp, rgb | 0xFF000000, h2, cam, prm, 768, 1024)
+    off = gpu_ctx.render(cam, fsb.default_params(filter=filt), mp, 768, 1024)
+    assert 0 < (on != off).mean() < 0.5          # the mode changes the picture, and only the blended spans
+    # tests-variant constants (z0 = 1: no z = 0 trap) still with the zero sentinel
+    prm2 = fsb.tests_variant_params(filter=filt, sentinel=0, flags=flags)
+    check(fsb, oracle, gpu_ctx, mp, rgb | 0xFF000000, h2, fsb.Camera(512, 800, 78, 0, 100, 800, 1, SKY), prm2, 400, 800)
+    mp.free()
+
+
+def test_smoothing_batch_and_errors(fsb, oracle, gpu_ctx, fbm1024):
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    prm = fsb.default_params(flags=fsb.FLAG_SMOOTHING)
+    cams = [fsb.Camera(*p, SKY) for p in POSES[:5]]
+    frames = gpu_ctx.render_batch(cams, prm, mp, 200, 320)
+    for cam, got in zip(cams, frames):
+        want = oracle.render(ocam(oracle, cam), oprm(oracle, prm), col, hgt & 0xFF, 200, 320)
+        assert np.array_equal(got, want)
+    with pytest.raises(fsb.FsbError):   # smoothing exists only in fut/voxel_renderer.fut (zero sentinel)
+        gpu_ctx.render(cams[0], fsb.default_params(sentinel=1, flags=fsb.FLAG_SMOOTHING), mp, 64, 64)
     mp.free()
