@@ -397,7 +397,36 @@ def run_ours(args, wl):
            "steps": e_steps, "ms_per_step": 1e3 * e_dt / e_steps,
            "api": "fsb_render_batch (pinned host frames; pose constants H2D + frames D2H inside the timed region)"}
 
-    extra = {}
+    # ---- secondary runs: other renderer variants on the same path, single-frame latency ----
+    def timed(prm_x, n_steps=5):
+        def f():
+            ctx.render_batch_device(cam_arr, prm_x, mp, h, w, out_dev)
+        f()
+        msx = time_device_steps(torch, ctx, st, f, n_steps, flush)
+        return total * n_steps / (max_over_ranks(sum(msx)) / 1e3)
+
+    secondary = {
+        "tests_variant_frames_per_s": timed(F.tests_variant_params()),   # z0 = 1, d = 0.005, nearest, sky sentinel, 240
+        "smoothing_on_frames_per_s": timed(F.default_params(flags=F.FLAG_SMOOTHING)),
+        "nearest_frames_per_s": timed(F.default_params(filter=0)),
+    }
+    single = F.Camera(m / 2 + 0.37, m / 2 + 0.73, max(160.0, float(hgt[m // 2, m // 2]) + 20.0), 2.2, 0.3 * h, dst, 1.2, SKY)
+
+    def one_frame():
+        ctx.render_device(single, prm, mp, h, w, out_dev)
+
+    one_frame()
+    ms1 = time_device_steps(torch, ctx, st, one_frame, 20, flush)
+    secondary["single_frame_cold_l2_us"] = 1e3 * sorted(ms1)[len(ms1) // 2]   # median; 3 launches, L2 flushed before each
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(50):
+        one_frame()
+    e1.record(st)
+    e1.synchronize()
+    secondary["single_frame_back_to_back_us"] = 1e3 * e0.elapsed_time(e1) / 50   # map L2-resident, launches queued
+
+    extra = {"secondary": secondary}
     cpu = None
     if rank == 0:
         extra["l2_stream_gbs"] = ctx.l2_stream_gbs()
@@ -579,9 +608,15 @@ def cpu_baseline(F, wl, col, hgt, total):
         O.render(camera_path(O, hgt, m, total, i, 1, h, dst)[0], prm, col, hgt, h, w, eval_all_colors=True, nthreads=0)
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+    # the `futhark c` (sequential backend) analogue: the same code on one thread, two poses
+    t1 = time.perf_counter()
+    for i in (0, total // 2):
+        O.render(camera_path(O, hgt, m, total, i, 1, h, dst)[0], prm, col, hgt, h, w, eval_all_colors=True, nthreads=1)
+    one = 2.0 / (time.perf_counter() - t1)
+    return {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "one_thread_value": one,
             "sample": "%d poses spread over the %d-pose path (%.1f s), C restatement of the reference (oracle/), "
-                      "OpenMP over columns, colour filter evaluated for every sample as the reference does" % (n, total, dt)}
+                      "OpenMP over columns, colour filter evaluated for every sample as the reference does; "
+                      "one_thread_value = 2 poses on a single thread" % (n, total, dt)}
 
 
 def main():

@@ -48,7 +48,7 @@ struct fsb_context {
 
 struct fsb_map {
   cudaArray_t array, array_h;     /* RGBA8 packed texels / R16F heights for the texture path */
-  cudaTextureObject_t tex, tex_h;
+  cudaTextureObject_t tex, tex_h, tex_f; /* tex_f: the RGBA8 array read as normalised floats (c/255, exact) */
   uint32_t *packed, *color;
   int32_t *height;
   int q, r;
@@ -295,6 +295,11 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
       td.readMode = cudaReadModeElementType;
       td.normalizedCoords = 1;
       e = cudaCreateTextureObject(&m->tex, &rd, &td, NULL);
+      if (e == cudaSuccess) {
+        td.readMode = cudaReadModeNormalizedFloat;
+        e = cudaCreateTextureObject(&m->tex_f, &rd, &td, NULL);
+        td.readMode = cudaReadModeElementType;
+      }
       /* heights alone as IEEE half (0..255 are exact): the march gathers 2-byte texels and gets floats */
       uint16_t *hh = (uint16_t *)malloc(n * 2);
       if (!hh) e = cudaErrorMemoryAllocation;
@@ -322,6 +327,7 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   if (e != cudaSuccess) {
     if (m->tex) cudaDestroyTextureObject(m->tex);
     if (m->tex_h) cudaDestroyTextureObject(m->tex_h);
+    if (m->tex_f) cudaDestroyTextureObject(m->tex_f);
     if (m->array) cudaFreeArray(m->array);
     if (m->array_h) cudaFreeArray(m->array_h);
     cudaFree(m->color); cudaFree(m->height); cudaFree(m->packed);
@@ -339,6 +345,7 @@ int fsb_map_free(fsb_context *ctx, fsb_map *m) {
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   if (m->tex) cudaDestroyTextureObject(m->tex);
   if (m->tex_h) cudaDestroyTextureObject(m->tex_h);
+  if (m->tex_f) cudaDestroyTextureObject(m->tex_f);
   if (m->array) cudaFreeArray(m->array);
   if (m->array_h) cudaFreeArray(m->array_h);
   cudaFree(m->color);
@@ -584,6 +591,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
   a.tex = map->tex;
   a.tex_h = map->tex_h;
+  a.tex_f = map->tex_f;
   a.inv_r = 1.0f / (float)map->r;
   a.inv_q = 1.0f / (float)map->q;
   int mem = FSB_MEM_PLANES;
@@ -598,7 +606,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (!((double)fabsf(cams[i].x) + reach < limit && (double)fabsf(cams[i].y) + reach < limit)) in_range = 0;
   }
   if (in_range && prm->f2i_mode == FSB_F2I_SATURATE && !(prm->flags & FSB_FLAG_FORCE_GENERIC)) {
-    if (map->tex && map->tex_h && !(prm->flags & FSB_FLAG_NO_TEXTURE)) mem = FSB_MEM_TEX;
+    if (map->tex && map->tex_h && map->tex_f && !(prm->flags & FSB_FLAG_NO_TEXTURE)) mem = FSB_MEM_TEX;
     else if (map->packed) mem = FSB_MEM_TILED;
   }
   CU(ctx, (cudaError_t)fsb_launch_march(&a, mem, ctx->stream, &ctx->launches));

@@ -33,6 +33,7 @@ typedef struct fsb_render_args {
   const uint32_t *packed;   /* height<<24 | rgb in 8x4-texel tiles (fsb_kernels.cu texel_x/texel_y), or NULL */
   int32_t xmask_hi, ymask_hi, log2r; /* tiled addressing: (r-1)&~7, (q-1)&~3, log2(r) */
   unsigned long long tex;   /* cudaTextureObject_t over an RGBA8 array of the packed texels (bytes B,G,R,height), or 0 */
+  unsigned long long tex_f; /* the same array read as normalised floats: a channel arrives as c/255, correctly rounded */
   unsigned long long tex_h; /* cudaTextureObject_t over an R16F array of the heights (exact for 0..255)                */
   float inv_r, inv_q;       /* 1/r, 1/q for normalised texture coordinates */
   const uint32_t *color;    /* [q][r] argb  */
