@@ -141,10 +141,13 @@ static int make_consts(const fsb_camera *cam, const fsb_params *prm, const fsb_m
    * rounding of its seven f32 operations -- 0.5 plus a relative 2e-6 covers any i32 height; rounded upward */
   const double hb = (double)map->hmax + 0.5 + fabs((double)map->hmax) * 2.0e-6;
   const float hbound = nextafterf((float)hb, INFINITY);
-  /* (only with the saturating conversion: the x86 / modern ones wrap huge rows to 0 and are not monotone) */
-  fc->cull_d = ((prm->flags & FSB_FLAG_NO_CULL) || prm->f2i_mode != FSB_F2I_SATURATE) ? -INFINITY
-                                                                                       : cam->height - hbound;
-  fc->cull_lane = 0;
+  /* Only with the saturating conversion (the x86 / modern ones wrap huge rows to 0 and are not monotone) and only
+   * while inv_z is positive and decreasing along the series: invz_param1 > 0 and z0 >= 0 (a negative z0 makes the
+   * first depths negative, fut/voxel_renderer.fut:33). */
+  const int monotone = prm->f2i_mode == FSB_F2I_SATURATE && prm->invz_param1 > 0.0f && prm->z0 >= 0.0f &&
+                       !(prm->flags & FSB_FLAG_NO_CULL);
+  fc->cull_d = monotone ? cam->height - hbound : -INFINITY;
+  fc->reserved = 0;
   return fc->n_z < 0 ? -1 : 0;
 }
 

@@ -20,7 +20,7 @@ typedef struct fsb_frame_consts {
   int32_t n_z;
   uint32_t sky, empty;          /* empty = 0 (zero sentinel) or sky (sky sentinel) */
   float cull_d;                 /* cam_h - (highest terrain + 0.5): no sample can project above this bound's row */
-  int32_t cull_lane;            /* lane of a 32-sample chunk whose inv_z minimises the bound (31 if cull_d >= 0 else 0) */
+  int32_t reserved;
 } fsb_frame_consts;
 
 #ifdef __CUDACC__

@@ -414,3 +414,18 @@ def test_smoothing_batch_and_errors(fsb, oracle, gpu_ctx, fbm1024):
     with pytest.raises(fsb.FsbError):   # smoothing exists only in fut/voxel_renderer.fut (zero sentinel)
         gpu_ctx.render(cams[0], fsb.default_params(sentinel=1, flags=fsb.FLAG_SMOOTHING), mp, 64, 64)
     mp.free()
+
+
+@pytest.mark.parametrize("filt", [1, 0])
+def test_occlusion_bound_needs_positive_decreasing_inv_z(fsb, oracle, gpu_ctx, fbm1024, filt):
+    """The terrain-height bound and the max-tap pre-test assume inv_z > 0 and decreasing along the depth series.
+    A negative invz_param1 flips the projection, a negative z0 makes the first depths negative
+    (fut/voxel_renderer.fut:33, :217): both must switch the shortcuts off, not produce different frames."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    for kw in (dict(invz_param1=-1.0), dict(invz_param1=-0.3, invz_param2=200.0), dict(z0=-0.4), dict(z0=-2.0, delta=0.01),
+               dict(invz_param1=0.0)):
+        prm = fsb.default_params(filter=filt, **kw)
+        for p in POSES[:4]:
+            check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 240, 320)
+    mp.free()
