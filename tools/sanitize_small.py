@@ -17,5 +17,11 @@ for flags in (0, F.FLAG_NO_TEXTURE, F.FLAG_FORCE_GENERIC, F.FLAG_NO_CULL):
 for f2i in (0, 1, 2):
     ctx.render(cams[1], F.default_params(f2i_mode=f2i), mp2, 64, 48)
 ctx.render(cams[2], F.tests_variant_params(), mp, 300, 40)
+for flags in (F.FLAG_SMOOTHING, F.FLAG_SMOOTHING | F.FLAG_FORCE_GENERIC, F.FLAG_SMOOTHING | F.FLAG_NO_TEXTURE):
+    ctx.render(cams[3], F.default_params(flags=flags), mp, 130, 170)
+    ctx.render_batch(cams, F.default_params(filter=0, flags=flags), mp, 33, 65)
+frame = ctx.render(cams[0], F.default_params(), mp, 64, 96)
+ctx.effect_interpolate(frame, 2)
+ctx.effect_interpolate(frame)
 ctx.bake_shadows(mp, F.sun_vector(1.2, 0.4), 64, 64)
 print("sanitize workload done, launches:", ctx.launch_count)
