@@ -429,3 +429,37 @@ def test_occlusion_bound_needs_positive_decreasing_inv_z(fsb, oracle, gpu_ctx, f
         for p in POSES[:4]:
             check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 240, 320)
     mp.free()
+
+
+def test_no_device_memory_leak_across_maps_contexts_and_sizes(fsb, gpu_ctx, fbm1024):
+    """Maps, contexts and the per-context scratch (depth tables, record lists, staging frames) are released: device
+    memory in use returns to where it started after many create / render / free cycles at changing sizes."""
+    import torch
+    col, hgt = fbm1024
+    cam = fsb.Camera(512.37, 512.73, 180, 2.2, 90, 400, 1.2, SKY)
+
+    def cycle(n):
+        for i in range(n):
+            ctx = fsb.Context(0)
+            mp = ctx.upload_map(col[: 256 + 64 * (i % 3), : 512 - 32 * (i % 2)].copy(), hgt[: 256 + 64 * (i % 3), : 512 - 32 * (i % 2)].copy())
+            h, w = 120 + 40 * (i % 4), 200 + 56 * (i % 3)
+            ctx.render(cam, fsb.default_params(flags=(i % 2) * fsb.FLAG_SMOOTHING), mp, h, w)
+            ctx.render_batch([cam] * 3, fsb.default_params(filter=i % 2), mp, h, w)
+            mp.free()
+            ctx.close()
+
+    cycle(3)                                   # warm the allocator / module state
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    cycle(24)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < (8 << 20), "device memory in use grew by %.1f MiB" % ((free0 - free1) / 2**20)
+    # same within one context: growing and shrinking frames must reuse or release the scratch, maps must be freed
+    before, _ = torch.cuda.mem_get_info()
+    for i in range(20):
+        mp = gpu_ctx.upload_map(col, hgt)
+        gpu_ctx.render(cam, fsb.default_params(), mp, 64 + 16 * (i % 5), 96)
+        mp.free()
+    after, _ = torch.cuda.mem_get_info()
+    assert before - after < (64 << 20)         # the context keeps its (bounded) scratch, nothing per map
