@@ -463,3 +463,19 @@ def test_no_device_memory_leak_across_maps_contexts_and_sizes(fsb, gpu_ctx, fbm1
         mp.free()
     after, _ = torch.cuda.mem_get_info()
     assert before - after < (64 << 20)         # the context keeps its (bounded) scratch, nothing per map
+
+
+def test_long_draw_distances(fsb, oracle, gpu_ctx, fbm1024):
+    """Depth series far longer than the bench configs (n_z = 10 954 and 31 622): table sizing, culling prefix search over
+    many chunks, record indices; plus the sample-index limit of the smoothing record word."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    for dist, h, w in ((60000.0, 96, 64), (500000.0, 40, 33)):
+        for flags in (0, fsb.FLAG_NO_CULL, fsb.FLAG_SMOOTHING):
+            cam = fsb.Camera(512.37, 512.73, 400 if dist > 1e5 else 120, 2.2, 0.4 * h, dist, 1.2, SKY)
+            check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(flags=flags), h, w)
+    assert len(fsb.get_zs(0.001, 1.0e7, 0.0)) > (1 << 17)
+    with pytest.raises(fsb.FsbError):      # 141 421 samples do not fit the 17-bit sample index of a smoothing record
+        gpu_ctx.render(fsb.Camera(512.37, 512.73, 120, 2.2, 20, 1.0e7, 1.2, SKY), fsb.default_params(flags=fsb.FLAG_SMOOTHING),
+                       mp, 32, 16)
+    mp.free()
