@@ -123,6 +123,31 @@ void futhark_context_free(struct futhark_context *ctx) {
   free(ctx->error);
   free(ctx);
 }
+int futhark_context_clear_caches(struct futhark_context *ctx) {
+  if (!ctx || !ctx->fsb) return fail(ctx, "no device context");
+  if (fsb_context_sync(ctx->fsb)) return fail_fsb(ctx);
+  flush_pending(ctx);
+  for (int i = 0; i < POOL_SLOTS; ++i)
+    if (ctx->pool[i].dev) {
+      fsb_device_free(ctx->fsb, ctx->pool[i].dev);
+      ctx->pool[i].dev = NULL;
+      ctx->pool[i].bytes = 0;
+    }
+  if (ctx->staging) fsb_host_free(ctx->fsb, ctx->staging);
+  ctx->staging = NULL;
+  ctx->staging_bytes = 0;
+  return 0;
+}
+char *futhark_context_report(struct futhark_context *ctx) {
+  char buf[256], name[128] = "no device";
+  if (ctx && ctx->fsb) fsb_context_device_name(ctx->fsb, name, sizeof name);
+  snprintf(buf, sizeof buf, "futspace_b200 on %s: %lld kernel launches\n", name,
+           (long long)(ctx && ctx->fsb ? fsb_context_launch_count(ctx->fsb) : 0));
+  return strdup(buf);
+}
+void futhark_context_pause_profiling(struct futhark_context *ctx) { (void)ctx; }
+void futhark_context_unpause_profiling(struct futhark_context *ctx) { (void)ctx; }
+
 int futhark_context_sync(struct futhark_context *ctx) {
   if (!ctx || !ctx->fsb) return fail(ctx, "no device context");
   if (fsb_context_sync(ctx->fsb)) return fail_fsb(ctx);

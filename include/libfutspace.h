@@ -38,6 +38,13 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg);
 void futhark_context_free(struct futhark_context *ctx);
 int futhark_context_sync(struct futhark_context *ctx);
 char *futhark_context_get_error(struct futhark_context *ctx);
+/* the housekeeping entries every generated library has (unused by c/interactive.c and liblys.c, provided so that
+ * other hosts written against libfutspace.h link): release cached device buffers; a malloc'ed one-line report;
+ * profiling pause / unpause (no-ops: this library has no background profiling) */
+int futhark_context_clear_caches(struct futhark_context *ctx);
+char *futhark_context_report(struct futhark_context *ctx);
+void futhark_context_pause_profiling(struct futhark_context *ctx);
+void futhark_context_unpause_profiling(struct futhark_context *ctx);
 
 /* arrays (c/interactive.c:50-56; outputs of `render`) */
 struct futhark_u32_2d *futhark_new_u32_2d(struct futhark_context *ctx, const uint32_t *data, int64_t dim0, int64_t dim1);
