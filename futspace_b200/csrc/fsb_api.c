@@ -41,6 +41,7 @@ struct fsb_context {
   int prof_pending;
   unsigned long long *stats_dev;  /* profiling counters: chunks evaluated, records emitted */
   void *recs;                     /* march -> expand record lists */
+  int force_rec8;                 /* env FSB_REC8: always 8-byte records */
   uint32_t *sidx;
   size_t recs_cap, sidx_cap;      /* bytes */
   char name[128];
@@ -164,6 +165,7 @@ int fsb_context_new(int device, fsb_context **out) {
   fsb_context *ctx = (fsb_context *)calloc(1, sizeof *ctx);
   if (!ctx) return FSB_ERR_NOMEM;
   ctx->device = device;
+  ctx->force_rec8 = getenv("FSB_REC8") != NULL;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   ctx->sm_count = prop.multiProcessorCount;
   snprintf(ctx->name, sizeof ctx->name, "%.127s", prop.name);
@@ -612,6 +614,10 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (map->tex && map->tex_h && map->tex_f && !(prm->flags & FSB_FLAG_NO_TEXTURE)) mem = FSB_MEM_TEX;
     else if (map->packed) mem = FSB_MEM_TILED;
   }
+  /* 4-byte records where every emitted colour has alpha 0xFF or is 0 (fsb_expand4_kernel); FSB_REC8=1 keeps the
+   * 8-byte format for A/B measurements */
+  a.rec4 = mem != FSB_MEM_PLANES && !a.smooth && (map->alpha_bits == 0u || map->alpha_bits == 0xFF000000u) &&
+           !ctx->force_rec8;
   CU(ctx, (cudaError_t)fsb_launch_march(&a, mem, ctx->stream, &ctx->launches));
   if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
   CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));

@@ -55,6 +55,7 @@ typedef struct fsb_render_args {
   uint32_t *sidx;           /* [n_poses][ncols][n_bands+1]: sidx[b] = #records with row >= b<<rb_shift */
   int32_t rec_cap;          /* = h (rows strictly decrease along a list)                               */
   int32_t n_bands, rb_shift;
+  int32_t rec4;             /* 1: 4-byte records (row & 31) << 24 | alpha flag << 31 | rgb (packed maps, alpha 0x00 / 0xFF) */
   int32_t smooth;           /* smoothing #on: record .x = row | sample index << 15 (fsb_expand_smooth_kernel) */
   unsigned long long *stats; /* optional (profiling): [0] += chunks of 32 samples evaluated, [1] += records emitted */
 } fsb_render_args;
