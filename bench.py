@@ -426,6 +426,24 @@ def run_ours(args, wl):
     e1.synchronize()
     secondary["single_frame_back_to_back_us"] = 1e3 * e0.elapsed_time(e1) / 50   # map L2-resident, launches queued
 
+    if args.workload == "cfg1":
+        # BASELINE config 1 names the reference's own converted map pair: C1W / D1 (committed copy, tests/golden/)
+        import numpy as np
+        gold = os.path.join(ROOT, "tests", "golden", "c1w_d1.npz")
+        if os.path.exists(gold):
+            z = np.load(gold)
+            rgb = (z["r"].astype(np.uint32) << 16) | (z["g"].astype(np.uint32) << 8) | z["b"].astype(np.uint32) | np.uint32(0xFF000000)
+            h2 = z["height"].astype(np.int32)
+            mp2 = ctx.upload_map(rgb, h2)
+            cams2 = camera_path(F, h2, 1024, total, rank, P, h, dst, stride=world)
+            arr2 = (F.Camera * P)(*cams2)
+
+            def f2():
+                ctx.render_batch_device(arr2, prm, mp2, h, w, out_dev)
+            f2()
+            ms2 = time_device_steps(torch, ctx, st, f2, 5, flush)
+            secondary["c1w_d1_map_frames_per_s"] = total * 5 / (max_over_ranks(sum(ms2)) / 1e3)
+            mp2.free()
     extra = {"secondary": secondary}
     cpu = None
     if rank == 0:

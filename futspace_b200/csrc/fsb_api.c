@@ -176,6 +176,12 @@ int fsb_context_new(int device, fsb_context **out) {
     free(ctx);
     return FSB_ERR_CUDA;
   }
+  /* the march's colour table lives in the module's global memory of this device; (re)filling it with the same
+   * values is harmless, and everything this context launches is ordered after it on ctx->stream */
+  if (fsb_launch_lut_init(ctx->stream) != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    free(ctx);
+    return FSB_ERR_CUDA;
+  }
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&ctx->rendered[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->copied[i], cudaEventDisableTiming);

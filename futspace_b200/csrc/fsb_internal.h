@@ -71,6 +71,7 @@ int fsb_launch_setup(const fsb_frame_consts *fc_dev, const fsb_frame_consts *sin
 #define FSB_MEM_TEX 2
 int fsb_launch_march(const fsb_render_args *a, int mem, void *stream, int64_t *launches);
 int fsb_launch_expand(const fsb_render_args *a, void *stream, int64_t *launches);
+int fsb_launch_lut_init(void *stream); /* fills the colour look-up table of the march (once per device, before any render) */
 int fsb_launch_shadow(const uint32_t *color, const int32_t *height, int q, int r, const float *sun, int out_q, int out_r,
                       uint32_t *out, void *stream, int64_t *launches);
 int fsb_launch_interpolate(const uint32_t *img, int h, int w, int mode, int pd, uint32_t *out, void *stream, int64_t *launches);
