@@ -173,12 +173,17 @@ int fsb_context_new(int device, fsb_context **out) {
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->fc_free, cudaEventDisableTiming) != cudaSuccess) {
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     free(ctx);
     return FSB_ERR_CUDA;
   }
   /* the march's colour table lives in the module's global memory of this device; (re)filling it with the same
    * values is harmless, and everything this context launches is ordered after it on ctx->stream */
   if (fsb_launch_lut_init(ctx->stream) != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    cudaEventDestroy(ctx->fc_free);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
     free(ctx);
     return FSB_ERR_CUDA;
   }
