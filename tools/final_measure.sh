@@ -15,4 +15,4 @@ ncu --set full --import-source on --clock-control none -k regex:fsb_expand -c 1 
     python tools/prof_batch.py 1080p 128 1 > $O/ncu2.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:fsb_march -c 1 -f -o $O/march_4k_single \
     python tools/prof_batch.py 4k 1 1 > $O/ncu3.log 2>&1
-tail -2 $O/ncu1.log $O/ncu2.log $O/ncu3.log
+for f in $O/ncu1.log $O/ncu2.log $O/ncu3.log; do tail -n 2 $f; done
