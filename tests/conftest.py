@@ -44,6 +44,16 @@ def c1w_d1():
 
 
 @pytest.fixture(scope="session")
+def real_maps(c1w_d1):
+    """Four of the reference's 29 map pairs (C1W/D1 plus tests/golden/make_golden_maps.py): name -> (rgb u32, height i32)."""
+    maps = {"C1W/D1": c1w_d1}
+    for n in (7, 13, 29):
+        z = np.load(os.path.join(HERE, "golden", "c%dw_d%d_pal.npz" % (n, n)))
+        maps["C%dW/D%d" % (n, n)] = (z["pal"][z["idx"]].astype(np.uint32), z["height"].astype(np.int32))
+    return maps
+
+
+@pytest.fixture(scope="session")
 def golden_frames():
     return np.load(os.path.join(HERE, "golden", "golden_frames.npz"))
 

@@ -176,3 +176,14 @@ def test_smoothing_on_two_formulations_agree(oracle, c1w_d1):
     assert changed >= 4
     with pytest.raises(RuntimeError):   # no smoothing in the sky-sentinel renderer (fut/voxel_renderer_new.fut)
         oracle.render(cam, oracle.default_params(smoothing=1, sentinel=1), col, hgt, 16, 16)
+
+
+def test_real_map_pairs_two_formulations(oracle, real_maps):
+    """The sequential march and the literal scan / scatter / scan pipeline agree on every committed real map pair."""
+    for name, (rgb, hgt) in real_maps.items():
+        cam = oracle.Camera(512, 800, 78, 0, 100, 300, 1, SKY)
+        for prm in (oracle.tests_variant_params(), oracle.default_params(), oracle.default_params(smoothing=1)):
+            col = rgb if prm.sentinel else rgb | np.uint32(0xFF000000)
+            a = oracle.render(cam, prm, col, hgt, 100, 160)
+            b = oracle.render_literal(cam, prm, col, hgt, 100, 160)
+            assert np.array_equal(a, b), name

@@ -479,3 +479,21 @@ def test_long_draw_distances(fsb, oracle, gpu_ctx, fbm1024):
         gpu_ctx.render(fsb.Camera(512.37, 512.73, 120, 2.2, 20, 1.0e7, 1.2, SKY), fsb.default_params(flags=fsb.FLAG_SMOOTHING),
                        mp, 32, 16)
     mp.free()
+
+
+def test_real_map_pairs(fsb, oracle, gpu_ctx, real_maps):
+    """the reference's own map pairs at the tests/futspace.fut camera (tests variant: nearest,
+    sky sentinel, no alpha in the colours) and at the demo's init camera (live variant, loader alpha 0xFF), plus smoothing."""
+    for name, (rgb, hgt) in real_maps.items():
+        mp = gpu_ctx.upload_map(rgb, hgt)                       # tools/png2data.py leaves alpha 0
+        cam = fsb.Camera(512, 800, 78, 0, 100, 800, 1, SKY)     # tests/futspace.fut:129-136
+        out = check(fsb, oracle, gpu_ctx, mp, rgb, hgt, cam, fsb.tests_variant_params(), 400, 800)
+        assert len(np.unique(out)) >= 2, name                    # (on C7W/D7 this camera sits inside the terrain)
+        mp.free()
+        col = rgb | 0xFF000000                                   # c/freeimage_futspace.h:52
+        mp = gpu_ctx.upload_map(col, hgt)
+        cam = fsb.Camera(0.98, 0.6, 58, 2.2, 200, 800, 1.2, SKY)  # fut/interactive.fut:29-36
+        cam.height = max(58.0, float(hgt[0, 0]))                # terrain_collision, :67-87
+        for flags in (0, fsb.FLAG_SMOOTHING, fsb.FLAG_NO_TEXTURE):
+            check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(flags=flags), 512, 640)
+        mp.free()
