@@ -497,3 +497,22 @@ def test_real_map_pairs(fsb, oracle, gpu_ctx, real_maps):
         for flags in (0, fsb.FLAG_SMOOTHING, fsb.FLAG_NO_TEXTURE):
             check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(flags=flags), 512, 640)
         mp.free()
+
+
+def test_host_batch_double_buffering_and_launch_groups(fsb, oracle, gpu_ctx, fbm1024, monkeypatch):
+    """fsb_render_batch splits a batch into 64 MB chunks copied out while the next chunk renders; the launch-group
+    size (FSB_GROUP_POSES) splits a device batch.  Every frame must equal the single-frame render whatever the split."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    prm = fsb.default_params()
+    h, w, n = 768, 1024, 50                      # 3 MiB frames: chunks of 21 poses -> three chunks, two staging buffers
+    cams = camera_path(fsb, 1024, n, 600)
+    batch = gpu_ctx.render_batch(cams, prm, mp, h, w)
+    for i in (0, 20, 21, 22, 41, 42, 49):        # chunk boundaries
+        assert np.array_equal(batch[i], gpu_ctx.render(cams[i], prm, mp, h, w)), i
+    monkeypatch.setenv("FSB_GROUP_POSES", "7")   # read per call (fsb_api.c group_size)
+    small = gpu_ctx.render_batch(cams[:20], prm, mp, 96, 128)
+    monkeypatch.delenv("FSB_GROUP_POSES")
+    ref = gpu_ctx.render_batch(cams[:20], prm, mp, 96, 128)
+    assert np.array_equal(small, ref)
+    mp.free()
