@@ -87,3 +87,24 @@ def test_sun_vector_matches_oracle(fsb, oracle, sh, sa):
     a, b = fsb.sun_vector(sh, sa), oracle.sun_vector(sh, sa)
     assert np.array_equal(np.float32(a), np.float32(b))
     assert abs(sum(x * x for x in a) - 1.0) < 1e-5
+
+
+def test_headers_compile_as_c_and_cxx_and_link(fsb, tmp_path):
+    """What a maintainer does first: include the two headers from C (c/interactive.c is C99-ish) and from C++, take the
+    address of every declared entry point and link against the shared library (no call is made: no GPU needed)."""
+    import subprocess
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    libdir = os.path.dirname(fsb.LIB_PATH)
+    decl = declared_symbols()
+    body = "\n".join("  p[%d] = (void (*)(void))%s;" % (i, n) for i, n in enumerate(decl))
+    src = ('#include <stdio.h>\n#include "futspace_b200.h"\n#include "libfutspace.h"\n'
+           "int main(void) {\n  void (*p[%d])(void);\n%s\n  printf(\"%%d\\n\", (int)(sizeof p / sizeof p[0]));\n  return p[0] == 0;\n}\n"
+           % (len(decl), body))
+    for name, cc, std in (("t.c", "/usr/bin/gcc", "-std=c99"), ("t.cpp", "/usr/bin/g++", "-std=c++11")):
+        f = tmp_path / name
+        f.write_text(src)
+        exe = tmp_path / (name + ".out")
+        subprocess.check_call([cc, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, str(f), "-o", str(exe),
+                               "-L", libdir, "-lfutspace_b200", "-Wl,-rpath," + libdir])
+        out = subprocess.check_output([str(exe)]).decode().strip()
+        assert int(out) == len(decl)
