@@ -365,6 +365,10 @@ def run_ours(args, wl):
                 "launch_ms": march_ms / march_n,
                 "kernel_share_of_step": march_ms / (march_ms + expand_ms + setup_ms),
                 "mode": "occlusion bound off (FSB_FLAG_NO_CULL): all W*n_z samples evaluated",
+                "note": "frac can exceed 1: the algorithmic gather bytes (16 B per depth sample) are served from L1/L2 -- "
+                        "neighbouring samples share 32-byte sectors of the 2-byte height texture -- so HBM is the nominal "
+                        "bound the contract asks for, not the limiter; ncu (profiles/r1_end_march_*) shows the kernel "
+                        "issue-bound: 76 % issue-active, XU pipe 60 %, DRAM 3.5 %",
                 "default_path": {"march_launch_ms": prof_cull["march"][0] / prof_cull["march"][1],
                                  "chunks_evaluated_frac": chunks_eval / max(1, chunks_full),
                                  "records_per_frame": records / (2.0 * P),
