@@ -89,6 +89,8 @@ SYMBOLS = {
     "fsb_device_free": (_ci, [_vp, _vp]),
     "fsb_host_malloc": (_ci, [_vp, _sz, _P(_vp)]),
     "fsb_host_free": (_ci, [_vp, _vp]),
+    "fsb_host_register": (_ci, [_vp, _vp, _sz]),
+    "fsb_host_unregister": (_ci, [_vp, _vp]),
     "fsb_copy_to_host": (_ci, [_vp, _vp, _vp, _sz]),
     "fsb_copy_to_device": (_ci, [_vp, _vp, _vp, _sz]),
     "fsb_ipc_export": (_ci, [_vp, _vp, _vp]),
@@ -310,6 +312,13 @@ class Context:
 
     def host_free(self, ptr):
         self._check(lib().fsb_host_free(self.handle, ptr))
+
+    def host_register(self, array):
+        """fsb_host_register on a numpy array the caller keeps alive (unregister before dropping it)."""
+        self._check(lib().fsb_host_register(self.handle, array.ctypes.data, array.nbytes))
+
+    def host_unregister(self, array):
+        self._check(lib().fsb_host_unregister(self.handle, array.ctypes.data))
 
     def copy_to_host(self, dst, src_dev, nbytes):
         self._check(lib().fsb_copy_to_host(self.handle, dst, src_dev, nbytes))

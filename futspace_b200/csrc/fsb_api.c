@@ -743,6 +743,23 @@ int fsb_host_free(fsb_context *ctx, void *ptr) {
   CU(ctx, cudaFreeHost(ptr));
   return FSB_OK;
 }
+/* Page-lock memory the caller already owns (the host's frame buffer, c/interactive.c:115) so that fsb_render /
+ * fsb_render_batch / fsb_copy_to_host move frames into it by DMA at full PCIe rate instead of through the driver's
+ * pageable staging path. */
+int fsb_host_register(fsb_context *ctx, void *ptr, size_t bytes) {
+  if (!ctx || !ptr || !bytes) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return FSB_OK;
+}
+int fsb_host_unregister(fsb_context *ctx, void *ptr) {
+  if (!ctx || !ptr) return FSB_ERR_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  CU(ctx, cudaHostUnregister(ptr));
+  return FSB_OK;
+}
 int fsb_copy_to_host(fsb_context *ctx, void *dst, const void *src, size_t bytes) {
   if (!ctx || !dst || !src) return FSB_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->device));

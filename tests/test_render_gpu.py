@@ -516,3 +516,22 @@ def test_host_batch_double_buffering_and_launch_groups(fsb, oracle, gpu_ctx, fbm
     ref = gpu_ctx.render_batch(cams[:20], prm, mp, 96, 128)
     assert np.array_equal(small, ref)
     mp.free()
+
+
+def test_registered_host_frame_buffer(fsb, oracle, gpu_ctx, fbm1024):
+    """fsb_host_register: the host's own frame buffer page-locked once (as a maintainer would do with lys's ctx->data),
+    frames rendered into it repeatedly, then released."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    buf = np.zeros((300, 400), np.uint32)
+    gpu_ctx.host_register(buf)
+    for p in POSES[:3]:
+        cam = fsb.Camera(*p, SKY)
+        out = gpu_ctx.render(cam, fsb.default_params(), mp, 300, 400, out=buf)
+        assert out is buf
+        want = oracle.render(ocam(oracle, cam), oprm(oracle, fsb.default_params()), col, hgt & 0xFF, 300, 400)
+        assert np.array_equal(buf, want)
+    gpu_ctx.host_unregister(buf)
+    with pytest.raises(fsb.FsbError):
+        gpu_ctx.host_unregister(buf)           # not registered any more: reported, not fatal
+    mp.free()
