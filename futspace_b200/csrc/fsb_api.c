@@ -145,8 +145,10 @@ static int make_consts(const fsb_camera *cam, const fsb_params *prm, const fsb_m
   /* Only with the saturating conversion (the x86 / modern ones wrap huge rows to 0 and are not monotone) and only
    * while inv_z is positive and decreasing along the series: invz_param1 > 0 and z0 >= 0 (a negative z0 makes the
    * first depths negative, fut/voxel_renderer.fut:33). */
-  const int monotone = prm->f2i_mode == FSB_F2I_SATURATE && prm->invz_param1 > 0.0f && prm->z0 >= 0.0f &&
-                       !(prm->flags & FSB_FLAG_NO_CULL);
+  /* ... and the multiplier too: a one-pixel-wide frame has f32(w/2) = 0, so inv_z is 0 everywhere except NaN
+   * (inf * 0) at z = 0 -- that one sample converts to row 0 and fills the column, whatever the bound says. */
+  const int monotone = prm->f2i_mode == FSB_F2I_SATURATE && prm->invz_param1 > 0.0f && fc->invz_mul > 0.0f &&
+                       prm->z0 >= 0.0f && !(prm->flags & FSB_FLAG_NO_CULL);
   fc->cull_d = monotone ? cam->height - hbound : -INFINITY;
   fc->reserved = 0;
   return fc->n_z < 0 ? -1 : 0;

@@ -535,3 +535,18 @@ def test_registered_host_frame_buffer(fsb, oracle, gpu_ctx, fbm1024):
     with pytest.raises(fsb.FsbError):
         gpu_ctx.host_unregister(buf)           # not registered any more: reported, not fatal
     mp.free()
+
+
+def test_one_pixel_wide_frame_with_horizon_below_the_frame(fsb, oracle, gpu_ctx, fbm1024):
+    """Found by tools/soak_fuzz.py: w = 1 makes f32(w/2) = 0, inv_z is then 0 for every sample (row = horizon) except the
+    z = 0 sample, whose inf * 0 = NaN converts to row 0 and fills the column; the occlusion bound must not skip it."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    for h, horizon, camh in ((27, 50.3, 453.0), (127, 158.8, 349.0), (64, 10.0, 300.0), (64, 64.0, 260.0)):
+        for filt in (0, 1):
+            for sentinel in (0, 1):
+                cam = fsb.Camera(-174.69, 251.43, camh, 5.7278, horizon, 782.67, 1.113, SKY)
+                check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(filter=filt, sentinel=sentinel), h, 1)
+    check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(300.5, 200.25, 400, 1.0, 90.0, 500, 1.2, SKY),
+          fsb.default_params(flags=fsb.FLAG_SMOOTHING), 40, 1)
+    mp.free()
