@@ -49,6 +49,17 @@ while time.time() - t0 < budget:
             cam.x, cam.y = float(int(cam.x)), float(int(cam.y))
         if rng.random() < 0.1:
             cam.x, cam.y = float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1))
+        u = rng.random()
+        if u < 0.05:       # far outside the fast paths' coordinate range: generic kernel
+            cam.x, cam.y = float(rng.uniform(-1e7, 1e7)), float(rng.uniform(-1e7, 1e7))
+        elif u < 0.10:     # extreme heights / horizons
+            cam.height, cam.horizon = float(rng.uniform(-1e4, 1e4)), float(rng.uniform(-1e4, 1e4))
+        elif u < 0.15:     # degenerate view: zero / negative field of view, tiny distance (n_z = 0 or 1), huge angle
+            cam.fov = float(rng.choice([0.0, -1.2, 1e-6]))
+            cam.distance = float(rng.choice([1e-5, 0.0011, 3.0, cam.distance]))
+            cam.angle = float(rng.uniform(-1e4, 1e4))
+        elif u < 0.20:     # sentinel collisions: the sky colour is a colour of the map
+            cam.sky_color = int(col[int(rng.integers(0, q)), int(rng.integers(0, r))])
         prm = F.default_params() if rng.random() < 0.7 else F.tests_variant_params()
         prm.filter = int(rng.integers(0, 2))
         prm.sentinel = int(rng.integers(0, 2))
