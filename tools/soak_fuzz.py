@@ -71,8 +71,25 @@ while time.time() - t0 < budget:
             prm.invz_param1, prm.invz_param2 = float(rng.uniform(-1.0, 3.0)), float(rng.uniform(1, 600))
         if rng.random() < 0.15:
             prm.z0, prm.delta = float(rng.uniform(-1.0, 3.0)), float(rng.uniform(0.0005, 0.05))
+        mode = int(rng.integers(0, 4))   # which entry point produces the frame
         try:
-            got = ctx.render(cam, prm, mp, h, w)
+            if mode == 0:
+                got = ctx.render(cam, prm, mp, h, w)
+            elif mode == 1:                # batch of three poses, the checked one in a random slot
+                others = [F.Camera(cam.x + 3.5, cam.y - 2.25, cam.height + 5, cam.angle + 0.3, cam.horizon, cam.distance * 0.5 + 1,
+                                   cam.fov, cam.sky_color) for _ in range(2)]
+                slot = int(rng.integers(0, 3))
+                cams3 = others[:slot] + [cam] + others[slot:]
+                got = ctx.render_batch(cams3, prm, mp, h, w)[slot]
+            else:                          # column slabs rendered separately into one padded device frame
+                stride = w + int(rng.integers(0, 5))
+                dev = ctx.device_malloc(h * stride * 4)
+                cut = int(rng.integers(0, w + 1))
+                for c0, c1 in ((0, cut), (cut, w)):
+                    if c1 > c0:
+                        ctx.render_columns_device(cam, prm, mp, h, w, c0, c1, dev + c0 * 4, stride)
+                got = ctx.download(dev, (h, stride))[:, :w].copy()
+                ctx.device_free(dev)
         except F.FsbError as e:
             kinds["error"] = kinds.get("error", 0) + 1
             continue
