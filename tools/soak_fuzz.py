@@ -10,6 +10,7 @@ import oracle_lib as O
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+tall = len(sys.argv) > 3 and sys.argv[3] == "tall"   # tall narrow frames, long depth series: many bands, long columns
 rng = np.random.default_rng(seed)
 ctx = F.Context(0)
 base_col, base_hgt = F.terrain_fbm(512)
@@ -42,9 +43,14 @@ while time.time() - t0 < budget:
     hm = (hgt & 0xFF) if mask else hgt
     for _ in range(6):
         h, w = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        if tall:
+            h, w = int(rng.integers(200, 1300)), int(rng.integers(1, 48))
         cam = F.Camera(float(rng.uniform(-600, 600)), float(rng.uniform(-600, 600)), float(rng.uniform(-50, 500)),
                        float(rng.uniform(-7, 7)), float(rng.uniform(-50, h + 50)), float(rng.uniform(0.01, 900)),
                        float(rng.uniform(0.2, 2.5)), int(rng.integers(0, 1 << 32)))
+        if tall:
+            cam.distance = float(rng.uniform(500, 4500))
+            cam.horizon = float(rng.uniform(0, h))
         if rng.random() < 0.15:
             cam.x, cam.y = float(int(cam.x)), float(int(cam.y))
         if rng.random() < 0.1:
