@@ -108,3 +108,28 @@ def test_headers_compile_as_c_and_cxx_and_link(fsb, tmp_path):
                                "-L", libdir, "-lfutspace_b200", "-Wl,-rpath," + libdir])
         out = subprocess.check_output([str(exe)]).decode().strip()
         assert int(out) == len(decl)
+
+
+def test_get_zs_random_agreement_with_oracle(fsb, oracle):
+    """Library and oracle agree on the depth series for random constants -- values, length, and which inputs are rejected
+    (negative z0 and tiny distances included)."""
+    rng = np.random.default_rng(7)
+    rejected = 0
+    for _ in range(3000):
+        delta = float(np.float32(rng.uniform(0.0005, 0.05)))
+        z0 = float(np.float32(rng.uniform(-1, 3)))
+        dist = float(np.float32(rng.choice([1e-5, 0.0011, 3.0, rng.uniform(0.01, 900)])))
+        try:
+            a = fsb.get_zs(delta, dist, z0)
+        except ValueError:
+            a = None
+        try:
+            b = oracle.get_zs(delta, dist, z0)
+        except ValueError:
+            b = None
+        assert (a is None) == (b is None), (delta, dist, z0)
+        if a is None:
+            rejected += 1
+        else:
+            assert np.array_equal(a, b), (delta, dist, z0)
+    assert 0 < rejected < 3000
