@@ -225,7 +225,7 @@ def run_reference(args, wl):
         "config": {"workload": wl["name"], "frame": [w, h], "map": m, "distance": dist, "filter": "bilinear",
                    "poses_per_step": n_ref},
         "mpixel_per_s": fps * w * h / 1e6,
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "cpu_model": cpu_model(), "kind": "port",
                          "sample": "%d of the %d path poses per step, C restatement of the reference (oracle/), "
                                    "OpenMP over columns, colour filter evaluated for every sample" % (n_ref, total)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -615,6 +615,16 @@ def run_colsplit(args, wl):
         dist.destroy_process_group()
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(F, wl, col, hgt, total):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
@@ -635,7 +645,8 @@ def cpu_baseline(F, wl, col, hgt, total):
     for i in (0, total // 2):
         O.render(camera_path(O, hgt, m, total, i, 1, h, dst)[0], prm, col, hgt, h, w, eval_all_colors=True, nthreads=1)
     one = 2.0 / (time.perf_counter() - t1)
-    return {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "one_thread_value": one,
+    return {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "cpu_model": cpu_model(), "kind": "port",
+            "one_thread_value": one,
             "sample": "%d poses spread over the %d-pose path (%.1f s), C restatement of the reference (oracle/), "
                       "OpenMP over columns, colour filter evaluated for every sample as the reference does; "
                       "one_thread_value = 2 poses on a single thread" % (n, total, dt)}
