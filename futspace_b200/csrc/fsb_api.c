@@ -71,8 +71,10 @@ static int set_err(fsb_context *ctx, int code, const char *fmt, ...) {
 #define CU(ctx, call)                                                                              \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess)                                                                         \
+    if (e_ != cudaSuccess) {                                                                       \
+      (void)cudaGetLastError(); /* a reported (non-sticky) error must not resurface at the next launch check */ \
       return set_err((ctx), FSB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    }                                                                                              \
   } while (0)
 
 /* ------------------------------------------------------------------------------------------ */
@@ -350,6 +352,7 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
     if (m->array_h) cudaFreeArray(m->array_h);
     cudaFree(m->color); cudaFree(m->height); cudaFree(m->packed);
     free(m);
+    (void)cudaGetLastError();
     return set_err(ctx, FSB_ERR_CUDA, "fsb_map_new: %s", cudaGetErrorString(e));
   }
   *out = m;
