@@ -281,18 +281,24 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
     return set_err(ctx, FSB_ERR_NOMEM, "fsb_map_new: out of host memory");
   }
   const uint32_t alpha = color[0] & 0xFF000000u;
-  for (size_t i = 0; i < n; ++i) {
-    int32_t hv = mask_heights ? (height[i] & 0xFF) : height[i];
-    hm[i] = hv;
-    if (i == 0 || hv > m->hmax) m->hmax = hv;
-    if (hv < 0 || hv > 255 || (color[i] & 0xFF000000u) != alpha) packable = 0;
-    pk_rm[i] = ((uint32_t)hv << 24) | (color[i] & 0x00FFFFFFu);
-    if (tileable) {
-      const size_t y = i / (size_t)r, x = i % (size_t)r;
-      const size_t t = ((y >> 2) * (size_t)(r >> 3) + (x >> 3)) * 32 + ((y & 3) << 3) + (x & 7);
-      pk[t] = pk_rm[i];
+  int32_t hmax = mask_heights ? (height[0] & 0xFF) : height[0];
+  /* rows in parallel: a 16384 x 16384 map is 268 M texels */
+#pragma omp parallel for schedule(static) reduction(max : hmax) reduction(&& : packable)
+  for (int y = 0; y < q; ++y) {
+    for (int x = 0; x < r; ++x) {
+      const size_t i = (size_t)y * (size_t)r + (size_t)x;
+      const int32_t hv = mask_heights ? (height[i] & 0xFF) : height[i];
+      hm[i] = hv;
+      if (hv > hmax) hmax = hv;
+      if (hv < 0 || hv > 255 || (color[i] & 0xFF000000u) != alpha) packable = 0;
+      pk_rm[i] = ((uint32_t)hv << 24) | (color[i] & 0x00FFFFFFu);
+      if (tileable) {
+        const size_t t = (((size_t)y >> 2) * (size_t)(r >> 3) + ((size_t)x >> 3)) * 32 + (((size_t)y & 3) << 3) + ((size_t)x & 7);
+        pk[t] = pk_rm[i];
+      }
     }
   }
+  m->hmax = hmax;
   m->alpha_bits = alpha;
   cudaError_t e = cudaMalloc((void **)&m->color, n * 4);
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->height, n * 4);
@@ -324,7 +330,8 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
       uint16_t *hh = (uint16_t *)malloc(n * 2);
       if (!hh) e = cudaErrorMemoryAllocation;
       if (e == cudaSuccess) {
-        for (size_t i = 0; i < n; ++i) hh[i] = half_bits_of_byte((uint32_t)hm[i]);
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)n; ++i) hh[i] = half_bits_of_byte((uint32_t)hm[i]);
         struct cudaChannelFormatDesc ch = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindFloat);
         e = cudaMallocArray(&m->array_h, &ch, (size_t)r, (size_t)q, cudaArrayTextureGather);
         if (e == cudaSuccess)
