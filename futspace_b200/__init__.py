@@ -27,6 +27,7 @@ FLAG_FORCE_GENERIC = 1
 FLAG_NO_TEXTURE = 2
 FLAG_NO_CULL = 4
 FLAG_SMOOTHING = 8
+FLAG_MARCH_Z = 16
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_RANGE, ERR_NO_DEVICE = range(6)
 
@@ -222,11 +223,11 @@ class Context:
         self._check(lib().fsb_context_set_profiling(self.handle, 1 if enable else 0))
 
     def get_profile(self):
-        """-> {"setup"|"march"|"expand": (total_ms, launches)} since the last call."""
-        ms = (ctypes.c_double * 3)()
-        n = (ctypes.c_int64 * 3)()
+        """-> {"setup"|"march"|"colour"|"expand": (total_ms, launch groups)} since the last call."""
+        ms = (ctypes.c_double * 4)()
+        n = (ctypes.c_int64 * 4)()
         self._check(lib().fsb_context_get_profile(self.handle, ms, n))
-        return {k: (ms[i], n[i]) for i, k in enumerate(("setup", "march", "expand"))}
+        return {k: (ms[i], n[i]) for i, k in enumerate(("setup", "march", "colour", "expand"))}
 
     def get_counters(self):
         """-> (chunks_evaluated, records) since the last call (profiling must be on)."""

@@ -35,15 +35,20 @@ struct fsb_context {
   uint32_t *frame_dev[2];
   size_t frame_cap[2];            /* pixels */
   int profiling;
-  cudaEvent_t pev[4];             /* profiling: before set-up, after set-up, after march, after expand */
-  double prof_ms[3];
-  int64_t prof_n[3];
+  cudaEvent_t pev[5];             /* profiling: before set-up, after set-up, after march, after colour, after expand */
+  double prof_ms[4];
+  int64_t prof_n[4];
   int prof_pending;
   unsigned long long *stats_dev;  /* profiling counters: chunks evaluated, records emitted */
   void *recs;                     /* march -> expand record lists */
   int force_rec8;                 /* env FSB_REC8: always 8-byte records */
   uint32_t *sidx;
   size_t recs_cap, sidx_cap;      /* bytes */
+  uint32_t *cand, *cand_cnt;      /* column-parallel march: candidate lists, their lengths, merge results */
+  uint4_fsb *seg_info;
+  size_t cand_cap, cand_cnt_cap, seg_info_cap; /* bytes */
+  const float *lut;               /* device address of the colour look-up table */
+  int force_march_z;              /* env FSB_MARCH_Z: always the lanes-over-depth march */
   char name[128];
 };
 
@@ -142,7 +147,10 @@ static int make_consts(const fsb_camera *cam, const fsb_params *prm, const fsb_m
   fc->empty = prm->sentinel == FSB_SENTINEL_SKY ? cam->sky_color : 0u;
   /* occlusion bound (fsb_kernels.cu): an interpolated height never exceeds the highest texel by more than the
    * rounding of its seven f32 operations -- 0.5 plus a relative 2e-6 covers any i32 height; rounded upward */
-  const double hb = (double)map->hmax + 0.5 + fabs((double)map->hmax) * 2.0e-6;
+  /* the bilinear sampler returns exactly 0 at integer coordinates (both weights 0), which lies above
+   * an all-negative (unmasked) terrain: the bound never drops below 0 */
+  const double hm = map->hmax > 0 ? (double)map->hmax : 0.0;
+  const double hb = hm + 0.5 + hm * 2.0e-6;
   const float hbound = nextafterf((float)hb, INFINITY);
   /* Only with the saturating conversion (the x86 / modern ones wrap huge rows to 0 and are not monotone) and only
    * while inv_z is positive and decreasing along the series: invz_param1 > 0 and z0 >= 0 (a negative z0 makes the
@@ -170,6 +178,7 @@ int fsb_context_new(int device, fsb_context **out) {
   if (!ctx) return FSB_ERR_NOMEM;
   ctx->device = device;
   ctx->force_rec8 = getenv("FSB_REC8") != NULL;
+  ctx->force_march_z = getenv("FSB_MARCH_Z") != NULL;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   ctx->sm_count = prop.multiProcessorCount;
   snprintf(ctx->name, sizeof ctx->name, "%.127s", prop.name);
@@ -195,6 +204,7 @@ int fsb_context_new(int device, fsb_context **out) {
     cudaEventCreateWithFlags(&ctx->rendered[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->copied[i], cudaEventDisableTiming);
   }
+  ctx->lut = fsb_lut_device_address();
   *out = ctx;
   return FSB_OK;
 }
@@ -211,9 +221,12 @@ void fsb_context_free(fsb_context *ctx) {
   cudaFree(ctx->frame_dev[1]);
   cudaFree(ctx->recs);
   cudaFree(ctx->sidx);
+  cudaFree(ctx->cand);
+  cudaFree(ctx->cand_cnt);
+  cudaFree(ctx->seg_info);
   cudaFree(ctx->stats_dev);
   cudaEventDestroy(ctx->fc_free);
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 5; ++i)
     if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
   for (int i = 0; i < 2; ++i) {
     cudaEventDestroy(ctx->rendered[i]);
@@ -438,29 +451,48 @@ static int ensure_tables(fsb_context *ctx, int n_poses, int tab_stride) {
 
 #define FSB_RB_SHIFT 5                   /* band of the per-column record index = 32 rows (fsb_expand_kernel) */
 #define FSB_MAX_H 32768
-#define FSB_SCRATCH_BUDGET ((size_t)4096 << 20)
+#define FSB_SCRATCH_BUDGET ((size_t)8192 << 20)
+#define FSB_COLS_MAX_NZ (1 << 17)        /* candidate word of the column-parallel march: row (15 bits) | sample index (17 bits) */
+#define FSB_MAX_SEG 32                   /* depth segments per column (fsb_merge_kernel: lane = segment) */
 
-static int ensure_scratch(fsb_context *ctx, int n_poses, int ncols, int h) {
+static int grow(fsb_context *ctx, void **ptr, size_t *cap, size_t need) {
+  if (need <= *cap) return FSB_OK;
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(*ptr);
+  *ptr = NULL;
+  *cap = 0;
+  CU(ctx, cudaMalloc(ptr, need));
+  *cap = need;
+  return FSB_OK;
+}
+
+/* How one launch group is rendered: which march, which record format, how the depth series is split. */
+typedef struct {
+  int mem;        /* FSB_MEM_* */
+  int cols;       /* column-parallel march (fsb_march_cols.cu) */
+  int rec4;       /* 4-byte records */
+  int n_seg;      /* warps per column's depth series */
+  int cand_cap;   /* candidate words per (column, segment) */
+  int ncols_pad;
+} render_plan;
+
+static int ensure_scratch(fsb_context *ctx, int n_poses, int ncols, int h, const render_plan *pl) {
   const int n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
-  const size_t need_r = (size_t)n_poses * ncols * (h + 1) * 8, need_s = (size_t)n_poses * ncols * (n_bands + 1) * 4;
-  if (need_r > ctx->recs_cap) {
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->recs);
-    ctx->recs = NULL; ctx->recs_cap = 0;
-    CU(ctx, cudaMalloc(&ctx->recs, need_r));
-    ctx->recs_cap = need_r;
-  }
-  if (need_s > ctx->sidx_cap) {
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->sidx);
-    ctx->sidx = NULL; ctx->sidx_cap = 0;
-    CU(ctx, cudaMalloc((void **)&ctx->sidx, need_s));
-    ctx->sidx_cap = need_s;
+  const size_t np = (size_t)n_poses;
+  int rc;
+  if ((rc = grow(ctx, &ctx->recs, &ctx->recs_cap, np * ncols * (h + 1) * (pl->rec4 ? 4 : 8)))) return rc;
+  if ((rc = grow(ctx, (void **)&ctx->sidx, &ctx->sidx_cap, np * ncols * (n_bands + 1) * 4))) return rc;
+  if (pl->cols) {
+    const size_t lists = np * pl->n_seg * pl->ncols_pad;
+    if ((rc = grow(ctx, (void **)&ctx->cand, &ctx->cand_cap, lists * pl->cand_cap * 4))) return rc;
+    if ((rc = grow(ctx, (void **)&ctx->cand_cnt, &ctx->cand_cnt_cap, lists * 4))) return rc;
+    if (pl->n_seg > 1 && (rc = grow(ctx, (void **)&ctx->seg_info, &ctx->seg_info_cap, lists * 16))) return rc;
   }
   return FSB_OK;
 }
 
-/* poses per launch group: bounded by the record-list scratch budget */
+/* poses per launch group: bounded by the record-list scratch budget (8 bytes per row and column: 4-byte candidates +
+ * 4-byte records, or 8-byte records alone) */
 static int group_size(int n, int ncols, int h) {
   size_t per = (size_t)ncols * (h + 1) * 8;
   size_t g = FSB_SCRATCH_BUDGET / (per ? per : 1);
@@ -486,8 +518,8 @@ static int check_common(fsb_context *ctx, const fsb_camera *cams, int n, const f
 /* profiling: fold the event deltas of the previous launch group into the accumulators */
 static int prof_collect(fsb_context *ctx) {
   if (!ctx->prof_pending) return FSB_OK;
-  CU(ctx, cudaEventSynchronize(ctx->pev[3]));
-  for (int i = 0; i < 3; ++i) {
+  CU(ctx, cudaEventSynchronize(ctx->pev[4]));
+  for (int i = 0; i < 4; ++i) {
     float ms = 0.f;
     CU(ctx, cudaEventElapsedTime(&ms, ctx->pev[i], ctx->pev[i + 1]));
     ctx->prof_ms[i] += ms;
@@ -501,7 +533,7 @@ int fsb_context_set_profiling(fsb_context *ctx, int enable) {
   if (!ctx) return FSB_ERR_ARG;
   CU(ctx, cudaSetDevice(ctx->device));
   if (enable && !ctx->pev[0])
-    for (int i = 0; i < 4; ++i) CU(ctx, cudaEventCreate(&ctx->pev[i]));
+    for (int i = 0; i < 5; ++i) CU(ctx, cudaEventCreate(&ctx->pev[i]));
   if (enable && !ctx->stats_dev) {
     CU(ctx, cudaMalloc((void **)&ctx->stats_dev, 16));
     CU(ctx, cudaMemsetAsync(ctx->stats_dev, 0, 16, ctx->stream));
@@ -528,7 +560,7 @@ int fsb_context_get_profile(fsb_context *ctx, double *ms, int64_t *launches) {
   if (!ctx || !ms || !launches) return FSB_ERR_ARG;
   int rc = prof_collect(ctx);
   if (rc) return rc;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
     ms[i] = ctx->prof_ms[i];
     launches[i] = ctx->prof_n[i];
     ctx->prof_ms[i] = 0.0;
@@ -572,7 +604,53 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
    * past the last chunk (fsb_kernels.cu) */
   const int tab_stride = 160 * ((max_nz + 31) / 32 + 6);
   if ((rc = ensure_tables(ctx, n, tab_stride))) return rc;
-  if ((rc = ensure_scratch(ctx, n, col_end - col_begin, h))) return rc;
+  /* ---- plan: which march, which record format, how the depth series is split ---- */
+  render_plan pl;
+  memset(&pl, 0, sizeof pl);
+  pl.mem = FSB_MEM_PLANES;
+  pl.n_seg = 1;
+  const int ncols = col_end - col_begin;
+  const int smooth = (prm->flags & FSB_FLAG_SMOOTHING) ? 1 : 0;
+  /* The texture path addresses texels with normalised coordinates (floor(x) + 1) / size and relies on that point
+   * staying within half a texel of the footprint centre.  For power-of-two sizes the division is exact; otherwise
+   * the two roundings cost up to 2^-23 * |coordinate| texels, so the coordinate range is kept where that is < 1/8.
+   * Beyond the range the generic kernel (integer addressing) renders the frame. */
+  const double limit = map->pow2 ? 4.0e6 : 1.0e6;
+  int in_range = 1;
+  for (int i = 0; i < n; ++i) {
+    const double reach = (double)fabsf(cams[i].distance) * (1.0 + (double)fabsf(cams[i].fov)) * 1.01 + 4.0;
+    if (!((double)fabsf(cams[i].x) + reach < limit && (double)fabsf(cams[i].y) + reach < limit)) in_range = 0;
+  }
+  if (in_range && prm->f2i_mode == FSB_F2I_SATURATE && !(prm->flags & FSB_FLAG_FORCE_GENERIC)) {
+    if (map->tex && map->tex_h && map->tex_f && !(prm->flags & FSB_FLAG_NO_TEXTURE)) pl.mem = FSB_MEM_TEX;
+    else if (map->packed) pl.mem = FSB_MEM_TILED;
+  }
+  /* 4-byte records where every emitted colour has alpha 0xFF or is 0 (fsb_expand4_kernel); FSB_REC8=1 keeps the
+   * 8-byte format for A/B measurements */
+  pl.rec4 = pl.mem != FSB_MEM_PLANES && !smooth && (map->alpha_bits == 0u || map->alpha_bits == 0xFF000000u) &&
+            !ctx->force_rec8;
+  /* The column-parallel march serves the texture path (the default for packable maps); the lanes-over-depth march of
+   * round 1 keeps the tiled / generic paths, very long series, and FSB_FLAG_MARCH_Z (A/B). */
+  pl.cols = pl.mem == FSB_MEM_TEX && max_nz <= FSB_COLS_MAX_NZ && !(prm->flags & FSB_FLAG_MARCH_Z) && !ctx->force_march_z;
+  pl.ncols_pad = (ncols + 31) & ~31;
+  const int n_chunks = (max_nz + 31) / 32;
+  if (pl.cols) {
+    /* enough warps to fill the device: one per 32 columns and depth segment; batches need no split */
+    const long long groups = (long long)(pl.ncols_pad / 32) * n;
+    const long long want = (long long)ctx->sm_count * 12;
+    long long seg = groups >= want ? 1 : (want + groups - 1) / groups;
+    if (seg > FSB_MAX_SEG) seg = FSB_MAX_SEG;
+    if (seg > n_chunks) seg = n_chunks;
+    if (seg < 1) seg = 1;
+    const char *env = getenv("FSB_SEGMENTS"); /* tuning aid: depth segments per column */
+    if (env && atoi(env) > 0) seg = atoi(env) > FSB_MAX_SEG ? FSB_MAX_SEG : atoi(env);
+    if (seg > n_chunks && n_chunks > 0) seg = n_chunks;
+    pl.n_seg = (int)seg;
+    const int seg_steps = 32 * ((n_chunks + pl.n_seg - 1) / pl.n_seg);
+    pl.cand_cap = seg_steps < h ? seg_steps : h;
+    if (pl.cand_cap < 1) pl.cand_cap = 1;
+  }
+  if ((rc = ensure_scratch(ctx, n, ncols, h, &pl))) return rc;
   if (n > 1) {
     CU(ctx, cudaMemcpyAsync(ctx->fc_dev, ctx->fc_host, sizeof(fsb_frame_consts) * (size_t)n, cudaMemcpyHostToDevice,
                             ctx->stream));
@@ -615,37 +693,35 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.sidx = ctx->sidx;
   a.rec_cap = h + 1; /* + the guard record */
   a.rb_shift = FSB_RB_SHIFT;
-  a.smooth = (prm->flags & FSB_FLAG_SMOOTHING) ? 1 : 0;
+  a.smooth = smooth;
   a.n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
   a.tex = map->tex;
   a.tex_h = map->tex_h;
   a.tex_f = map->tex_f;
   a.inv_r = 1.0f / (float)map->r;
   a.inv_q = 1.0f / (float)map->q;
-  int mem = FSB_MEM_PLANES;
-  /* The texture path addresses texels with normalised coordinates (floor(x) + 1) / size and relies on that point
-   * staying within half a texel of the footprint centre.  For power-of-two sizes the division is exact; otherwise
-   * the two roundings cost up to 2^-23 * |coordinate| texels, so the coordinate range is kept where that is < 1/8.
-   * Beyond the range the generic kernel (integer addressing) renders the frame. */
-  const double limit = map->pow2 ? 4.0e6 : 1.0e6;
-  int in_range = 1;
-  for (int i = 0; i < n; ++i) {
-    const double reach = (double)fabsf(cams[i].distance) * (1.0 + (double)fabsf(cams[i].fov)) * 1.01 + 4.0;
-    if (!((double)fabsf(cams[i].x) + reach < limit && (double)fabsf(cams[i].y) + reach < limit)) in_range = 0;
+  a.rec4 = pl.rec4;
+  a.full_eval = (prm->flags & FSB_FLAG_NO_CULL) ? 1 : 0;
+  a.lut = ctx->lut;
+  a.cand = ctx->cand;
+  a.cand_cnt = ctx->cand_cnt;
+  a.seg_info = ctx->seg_info;
+  a.n_seg = pl.n_seg;
+  a.cand_cap = pl.cand_cap;
+  a.ncols_pad = pl.ncols_pad;
+  if (pl.cols) {
+    /* few warps per SM (split series): deeper gather pipeline per warp */
+    CU(ctx, (cudaError_t)fsb_launch_march_cols(&a, pl.n_seg > 1, ctx->stream, &ctx->launches));
+    if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
+    CU(ctx, (cudaError_t)fsb_launch_colour(&a, ctx->stream, &ctx->launches));
+  } else {
+    CU(ctx, (cudaError_t)fsb_launch_march(&a, pl.mem, ctx->stream, &ctx->launches));
+    if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
   }
-  if (in_range && prm->f2i_mode == FSB_F2I_SATURATE && !(prm->flags & FSB_FLAG_FORCE_GENERIC)) {
-    if (map->tex && map->tex_h && map->tex_f && !(prm->flags & FSB_FLAG_NO_TEXTURE)) mem = FSB_MEM_TEX;
-    else if (map->packed) mem = FSB_MEM_TILED;
-  }
-  /* 4-byte records where every emitted colour has alpha 0xFF or is 0 (fsb_expand4_kernel); FSB_REC8=1 keeps the
-   * 8-byte format for A/B measurements */
-  a.rec4 = mem != FSB_MEM_PLANES && !a.smooth && (map->alpha_bits == 0u || map->alpha_bits == 0xFF000000u) &&
-           !ctx->force_rec8;
-  CU(ctx, (cudaError_t)fsb_launch_march(&a, mem, ctx->stream, &ctx->launches));
-  if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
+  if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[3], ctx->stream));
   CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));
   if (ctx->profiling) {
-    CU(ctx, cudaEventRecord(ctx->pev[3], ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->pev[4], ctx->stream));
     ctx->prof_pending = 1;
   }
   return FSB_OK;

@@ -1,0 +1,355 @@
+/*
+ * fsb_march_cols.cu -- the column-parallel march of the texture fast path (sm_100a).
+ *
+ *   fsb_marchc_kernel   lane = screen column, the warp walks the depth series; per-lane y-buffer in a register;
+ *                       emits, per column, the candidate list (row | sample index << 15)          fut/voxel_renderer.fut:215-231
+ *   fsb_merge_kernel    (depth range split over several warps only) which candidates of a segment survive the
+ *                       y-buffer carried in from the nearer segments, and where they land in the column's list  :231
+ *   fsb_colour_kernel   one thread per visible record: png_color / png_color_filtered (3 x argb.mix) and the band index
+ *                       of the list -> the (row, colour) records fsb_expand*_kernel consumes      fut/render_functions.fut:91-105
+ *
+ * Why this shape (round 2; the round-1 march, lanes over 32 consecutive depth samples of ONE column, stays in
+ * fsb_kernels.cu for the tiled / generic paths and as the A/B reference, FSB_FLAG_MARCH_Z):
+ *   - ncu on the round-1 march: 84 warp instructions per 32 samples, 77 % issue-active -- the occlusion scan
+ *     (`scan occlude`, :231) cost a REDUX, five SHFL+IMNMX, a ballot and a shared-memory queue per chunk, and every lane
+ *     loaded its own depth-table entry.  With lane = column the depth-table entry is warp-uniform (two broadcast loads per
+ *     step), `occlude` is one compare against the lane's own running minimum, and a sample that does not lower it
+ *     costs nothing more.
+ *   - The colour filter (33 divides + 9 square roots per sample in the reference) only runs for samples that are
+ *     visible, on full warps, in its own pass: the march keeps no colour state, which is what lets it run at 40+
+ *     warps per SM.
+ *   - A column's depth range can be split over S warps (single frames: 60 column groups cannot fill 148 SMs).  Each
+ *     segment marches against its own y-buffer; a candidate of segment s is visible iff its row is below the minimum
+ *     of all nearer segments (`occlude` is associative, :69-72) -- rows decrease along a list, so the survivors are a
+ *     suffix, found by one binary search per (column, segment) in fsb_merge_kernel.
+ *
+ * Float discipline as in fsb_kernels.cu: every parity-relevant operation uses the round-to-nearest intrinsics.
+ */
+#include <stdlib.h>
+
+#include "fsb_device.cuh"
+
+#define FSB_MC_WARPS 4 /* warps (= groups of 32 columns) per march CTA */
+
+/* One depth step of one column: the four heights of the bilinear footprint (or the single nearest height in h00) and
+ * the weights, fut/render_functions.fut:67-77 / :63-64.  Kept in registers between the gather and its use. */
+template <bool BIL>
+struct col_step {
+  float h00, h01, h10, h11;
+  float wx0, wx1, wy0, wy1;
+};
+
+/* get_segment (fut/voxel_renderer.fut:63-66) + the gather of png_height(_filtered).
+ * Bilinear weights: wx1 = x - floor x as written.  wx0 = ceil x - x without a second FRND on the XU pipe:
+ * ceil x = floor x + (x > floor x ? 1 : 0), exact below 2^23 -- one FSET.  The same corner addresses the gather: for a
+ * non-integer x it is floor x + 1, the common corner of the footprint {floor, floor + 1} (see FSB_TLD4); for an integer x
+ * both weights are 0, every product is +0 (heights are 0..255) and the texels fetched do not reach the result
+ * (SURVEY.md fact 9), so the footprint may be anything. */
+template <bool BIL>
+__device__ __forceinline__ void cstep_issue(col_step<BIL> &t, const fsb_render_args &a, const float4 l, float fj) {
+  const float x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
+  const float y = __fadd_rn(l.y, __fmul_rn(fj, l.w));
+  if (BIL) {
+    const float fx = floorf(x), fy = floorf(y);
+    t.wx1 = __fsub_rn(x, fx);
+    t.wy1 = __fsub_rn(y, fy);
+    const float cx = __fadd_rn(fx, t.wx1 > 0.0f ? 1.0f : 0.0f), cy = __fadd_rn(fy, t.wy1 > 0.0f ? 1.0f : 0.0f);
+    FSB_TLD4_F32(a.tex_h, __fmul_rn(cx, a.inv_r), __fmul_rn(cy, a.inv_q), t.h10, t.h11, t.h01, t.h00);
+    t.wx0 = __fsub_rn(cx, x);
+    t.wy0 = __fsub_rn(cy, y);
+  } else { /* i32.f32 truncates toward zero, then floored modulo = the texture unit's wrap (fut/render_functions.fut:63-64) */
+    const float u = __fmul_rn(__fadd_rn(truncf(x), 0.5f), a.inv_r), v = __fmul_rn(__fadd_rn(truncf(y), 0.5f), a.inv_q);
+    float g, b, al;
+    asm volatile("tex.2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6}];"
+                 : "=f"(t.h00), "=f"(g), "=f"(b), "=f"(al)
+                 : "l"(a.tex_h), "f"(u), "f"(v));
+  }
+}
+
+template <bool BIL>
+__device__ __forceinline__ float cstep_height(const col_step<BIL> &t) {
+  if (!BIL) return t.h00;
+  const float xi1 = __fadd_rn(__fmul_rn(t.wx0, t.h00), __fmul_rn(t.wx1, t.h01));
+  const float xi2 = __fadd_rn(__fmul_rn(t.wx0, t.h10), __fmul_rn(t.wx1, t.h11));
+  return __fadd_rn(__fmul_rn(t.wy0, xi1), __fmul_rn(t.wy1, xi2));
+}
+
+/* Per-lane march state: the y-buffer of :231 as a float (exact: rows <= 32768; -inf once it reached row 0 -- y >= 0
+ * always, :225, so nothing can pass `y < 0` any more) and the append pointer of the column's candidate list. */
+struct col_state {
+  float ybuf_f;
+  uint32_t *list;
+  int n;
+};
+
+/* Projection and occlusion test of one sample (fut/voxel_renderer.fut:223-225, `occlude` :69-72).
+ * With the saturating i32.f32 and an integer y-buffer Y >= 1:  max(0, i32.f32 rel) < Y  <=>  !(rel >= Y)  (a NaN converts
+ * to row 0), so the conversion only runs -- behind a warp-uniform branch -- when some column of the group sees the sample.
+ * A finished column (-inf) is passed only by a NaN; the exact test in the visible path rejects it. */
+template <bool BIL>
+__device__ __forceinline__ void cstep_resolve(const col_step<BIL> &t, float iz, float cam_h, float horizon, uint32_t kword,
+                                              col_state &st) {
+  const float rel = __fadd_rn(__fmul_rn(__fsub_rn(cam_h, cstep_height<BIL>(t)), iz), horizon);
+  const bool cand = !(rel >= st.ybuf_f);
+  if (__any_sync(FSB_FULL, cand)) {
+    const int yy = max(0, __float2int_rz(rel));
+    const float yf = (float)yy;
+    if (cand && yf < st.ybuf_f) {
+      st.list[st.n++] = (uint32_t)yy | kword;
+      st.ybuf_f = yy > 0 ? yf : -INFINITY;
+    }
+  }
+}
+
+/* U = depth steps per register set; two sets are in flight (the gathers of one are issued before the other is resolved). */
+template <bool BIL, int U, int MINB>
+__global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(const fsb_render_args a) {
+  static_assert(32 % (2 * U) == 0, "a pair of register sets must tile a 32-step table block");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pose = blockIdx.z, seg = blockIdx.y;
+  const int ncols = a.col_end - a.col_begin;
+  const int jrel = (blockIdx.x * FSB_MC_WARPS + warp) * 32 + lane;
+  if (jrel - lane >= ncols) return;
+  /* lanes past the last column of a ragged group march a column of their own into the padding of the scratch lists
+   * (ncols_pad): no masking in the loop, and nobody reads those lists */
+  const fsb_frame_consts *fcp = a.fc + pose;
+  const float cam_h = fcp->cam_h, horizon = fcp->horizon, cull_d = fcp->cull_d;
+  const int n_chunks = (fcp->n_z + 31) >> 5;
+  const float *tab = a.table + (size_t)pose * a.tab_stride;
+  const size_t lid = ((size_t)pose * a.n_seg + seg) * a.ncols_pad + jrel;
+  col_state st;
+  st.ybuf_f = (float)a.h;
+  st.list = a.cand + lid * a.cand_cap;
+  st.n = 0;
+  const float fj = (float)(a.col_begin + jrel);
+
+  /* this warp's share of the depth series, in table blocks of 32 samples */
+  int c_first = (int)(((long long)n_chunks * seg) / a.n_seg);
+  const int c_end = (int)(((long long)n_chunks * (seg + 1)) / a.n_seg);
+  /* Occlusion bound (see fsb_kernels.cu): camera above the highest terrain -> a prefix of the series projects below the
+   * bottom row and is skipped (lane = chunk, bound at the chunk's last sample) ... */
+  if (cull_d >= 0.0f && cull_d < INFINITY) {
+    int first = c_end;
+    for (int base = c_first; base < c_end; base += 32) {
+      const int ci = min(base + lane, c_end - 1);
+      const float izl = __ldg(tab + (size_t)ci * FSB_TAB_BLOCK + 128 + 31);
+      const bool below = max(0, __float2int_rz(__fadd_rn(__fmul_rn(cull_d, izl), horizon))) >= a.h;
+      const unsigned alive = __ballot_sync(FSB_FULL, !below);
+      if (alive) {
+        first = base + __ffs(alive) - 1;
+        break;
+      }
+    }
+    c_first = first;
+  }
+  /* ... camera below it -> the bound grows with depth: a column whose y-buffer it has reached is finished */
+  const bool can_stop = cull_d < 0.0f && cull_d > -INFINITY;
+  int c_done = 0;
+  if (c_first < c_end) {
+    col_step<BIL> sa[U], sb[U];
+    const float4 *bl = reinterpret_cast<const float4 *>(tab + (size_t)c_first * FSB_TAB_BLOCK);
+    asm volatile("" : "+l"(bl));
+#pragma unroll
+    for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, __ldg(bl + u), fj);
+    for (int c = c_first; c < c_end; ++c) {
+      const float *bz = reinterpret_cast<const float *>(bl) + 128; /* the block's 32 inv_z (:217) */
+      if (!a.full_eval) {
+        float bound = 0.0f;
+        if (can_stop) bound = (float)max(0, __float2int_rz(__fadd_rn(__fmul_rn(cull_d, __ldg(bz)), horizon)));
+        if (!__any_sync(FSB_FULL, st.ybuf_f > bound)) break; /* every column of the group is finished */
+      }
+      ++c_done;
+      const uint32_t kw = (uint32_t)(c << 5) << FSB_ROW_BITS;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2 * U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) cstep_issue<BIL>(sb[u], a, __ldg(bl + i + U + u), fj);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          cstep_resolve<BIL>(sa[u], __ldg(bz + i + u), cam_h, horizon, kw + ((uint32_t)(i + u) << FSB_ROW_BITS), st);
+        /* next set: the following steps of this block, or the head of the next block (the table is padded with
+         * blocks that repeat the last sample: a repeated sample projects to the same row and `occlude` keeps the
+         * earlier one) */
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          cstep_issue<BIL>(sa[u], a, __ldg(bl + (i + 2 * U < 32 ? i + 2 * U + u : FSB_TAB_BLOCK / 4 + u)), fj);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          cstep_resolve<BIL>(sb[u], __ldg(bz + i + U + u), cam_h, horizon, kw + ((uint32_t)(i + U + u) << FSB_ROW_BITS), st);
+      }
+      bl += FSB_TAB_BLOCK / 4;
+      /* the block pointer is warp-uniform; kept in a vector register pair (opaque to the compiler) the 40 loads of a
+       * block address it as [R + imm] instead of copying a uniform register pair in front of every load */
+      asm volatile("" : "+l"(bl));
+    }
+  }
+  a.cand_cnt[lid] = (uint32_t)st.n;
+  if (a.stats) {
+    /* in chunks of 32 samples of one column, like the lanes-over-depth march counts them */
+    if (lane == 0) atomicAdd(a.stats, (unsigned long long)c_done * (unsigned long long)min(32, ncols - (jrel - lane)));
+    const unsigned long long n = (jrel < ncols) ? (unsigned long long)st.n : 0ull;
+    unsigned long long tot = n;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) tot += __shfl_xor_sync(FSB_FULL, tot, d);
+    if (lane == 0) atomicAdd(a.stats + 1, tot);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Merge (n_seg > 1): one warp per (pose, column), lane = segment.  The carry into segment s is the minimum row of all
+ * nearer segments (or h); its candidates with row < carry are visible -- a suffix, rows decrease along a list. */
+__global__ void __launch_bounds__(128) fsb_merge_kernel(const fsb_render_args a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pose = blockIdx.y;
+  const int ncols = a.col_end - a.col_begin;
+  const int col = blockIdx.x * 4 + warp;
+  if (col >= ncols) return;
+  const int S = a.n_seg;
+  const size_t lid = ((size_t)pose * S + min(lane, S - 1)) * a.ncols_pad + col;
+  const uint32_t *list = a.cand + lid * a.cand_cap;
+  const int n = lane < S ? (int)a.cand_cnt[lid] : 0;
+  const int fin = n ? (int)(list[n - 1] & FSB_ROW_MASK) : a.h;
+  int incl = fin;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(FSB_FULL, incl, d);
+    if (lane >= d) incl = min(incl, o);
+  }
+  int carry = __shfl_up_sync(FSB_FULL, incl, 1);
+  if (lane == 0) carry = a.h;
+  int lo = 0, hi = n; /* first index with row < carry */
+  while (__any_sync(FSB_FULL, lo < hi)) {
+    if (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((int)(list[mid] & FSB_ROW_MASK) >= carry) lo = mid + 1;
+      else hi = mid;
+    }
+  }
+  const int vis = n - lo;
+  int off = vis;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(FSB_FULL, off, d);
+    if (lane >= d) off += o;
+  }
+  const int total = __shfl_sync(FSB_FULL, off, 31);
+  if (lane < S) a.seg_info[lid] = make_uint4((uint32_t)lo, (uint32_t)(off - vis), (uint32_t)carry, (uint32_t)vis);
+  /* bands at or above the last visible record: every record of the list has a row >= theirs */
+  const int last_row = __shfl_sync(FSB_FULL, incl, 31);
+  const int last_band = total ? (last_row >> a.rb_shift) : a.n_bands;
+  uint32_t *sidx = a.sidx + ((size_t)pose * ncols + col) * (a.n_bands + 1);
+  for (int b = lane; b <= last_band; b += 32) sidx[b] = (uint32_t)total;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Colour: one warp per (pose, column[, segment]), lane = record.  Reads the sample index, rebuilds the sample position
+ * (get_segment, :63-66), runs png_color / png_color_filtered and writes the record the expand kernels consume, plus the
+ * per-band index of the list (sidx[b] = number of records with row >= b * 32; rows strictly decrease along the list). */
+template <bool BIL>
+__global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a) {
+  const float *un = a.lut, *sq = a.lut + 256;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pose = blockIdx.z, seg = blockIdx.y;
+  const int ncols = a.col_end - a.col_begin;
+  const int col = blockIdx.x * 4 + warp;
+  if (col >= ncols) return;
+  const size_t lid = ((size_t)pose * a.n_seg + seg) * a.ncols_pad + col;
+  const uint32_t *src = a.cand + lid * a.cand_cap;
+  int n, off = 0, prev_band = a.n_bands;
+  if (a.n_seg > 1) {
+    const uint4 info = a.seg_info[lid];
+    src += info.x;
+    off = (int)info.y;
+    if ((int)info.z < a.h) prev_band = (int)(info.z >> a.rb_shift);
+    n = (int)info.w;
+  } else {
+    n = (int)a.cand_cnt[lid];
+  }
+  const size_t colid = (size_t)pose * ncols + col;
+  uint32_t *sidx = a.sidx + colid * (a.n_bands + 1);
+  uint32_t *rec4 = reinterpret_cast<uint32_t *>(a.recs) + colid * a.rec_cap + 1;
+  uint2 *rec8 = a.recs + colid * a.rec_cap + 1;
+  if (seg == 0 && lane == 0) { /* slot 0: the guard record the 8-byte walks stop at (see fsb_kernels.cu) */
+    if (a.rec4) rec4[-1] = 0u;
+    else rec8[-1] = make_uint2(0xffffffffu, 0u);
+  }
+  const float *tab = a.table + (size_t)pose * a.tab_stride;
+  const float fj = (float)(a.col_begin + col);
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < n;
+    uint32_t word = 0, colour = 0;
+    if (valid) {
+      word = src[i];
+      const uint32_t k = word >> FSB_ROW_BITS;
+      const float4 l = __ldg(reinterpret_cast<const float4 *>(tab + (size_t)(k >> 5) * FSB_TAB_BLOCK) + (k & 31));
+      const float x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
+      const float y = __fadd_rn(l.y, __fmul_rn(fj, l.w));
+      colour = sample_color<MEM_TEX, BIL, FSB_F2I_SATURATE>(a, x, y, un, sq);
+      const uint32_t row = word & FSB_ROW_MASK;
+      if (a.rec4) rec4[off + i] = (colour & 0x80FFFFFFu) | ((row & 31u) << 24);
+      else rec8[off + i] = make_uint2(a.smooth ? word : row, colour);
+    }
+    const int band = (int)((word & FSB_ROW_MASK) >> a.rb_shift);
+    int pb = __shfl_up_sync(FSB_FULL, band, 1);
+    if (lane == 0) pb = prev_band;
+    if (valid)
+      for (int b = band + 1; b <= pb; ++b) sidx[b] = (uint32_t)(off + i);
+    prev_band = __shfl_sync(FSB_FULL, band, min(n - base, 32) - 1);
+  }
+  /* unsplit series: bands at or above the last record */
+  if (a.n_seg == 1)
+    for (int b = lane; b <= prev_band; b += 32) sidx[b] = (uint32_t)n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+template <bool BIL, int U, int MINB>
+static int launch_marchc_t(const fsb_render_args &a, cudaStream_t s) {
+  const int ncols = a.col_end - a.col_begin;
+  dim3 grid((ncols + FSB_MC_WARPS * 32 - 1) / (FSB_MC_WARPS * 32), a.n_seg, a.n_poses);
+  fsb_marchc_kernel<BIL, U, MINB><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int fsb_launch_march_cols(const fsb_render_args *a, int deep, void *stream, int64_t *launches) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool bil = a->filter == FSB_FILTER_BILINEAR;
+  /* tuning aid: FSB_MARCHC_VARIANT = steps per register set / CTAs per SM of the bilinear march */
+  static int variant = -1;
+  if (variant < 0) {
+    const char *e = getenv("FSB_MARCHC_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  int rc;
+  if (bil && variant == 1) rc = launch_marchc_t<true, 4, 5>(*a, s);
+  else if (bil && variant == 2) rc = launch_marchc_t<true, 2, 8>(*a, s);
+  else if (bil && variant == 3) rc = launch_marchc_t<true, 2, 10>(*a, s);
+  else if (bil && variant == 4) rc = launch_marchc_t<true, 8, 2>(*a, s);
+  else if (bil && variant == 5) rc = launch_marchc_t<true, 4, 6>(*a, s);
+  else if (bil && variant == 6) rc = launch_marchc_t<true, 4, 4>(*a, s);
+  else if (deep) /* few warps per SM (single frames): more gathers in flight per warp */
+    rc = bil ? launch_marchc_t<true, 8, 2>(*a, s) : launch_marchc_t<false, 8, 2>(*a, s);
+  else
+    rc = bil ? launch_marchc_t<true, 4, 6>(*a, s) : launch_marchc_t<false, 4, 6>(*a, s);
+  if (launches) ++*launches;
+  return rc;
+}
+
+extern "C" int fsb_launch_colour(const fsb_render_args *a, void *stream, int64_t *launches) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ncols = a->col_end - a->col_begin;
+  if (a->n_seg > 1) {
+    dim3 mg((ncols + 3) / 4, a->n_poses);
+    fsb_merge_kernel<<<mg, 128, 0, s>>>(*a);
+    if (launches) ++*launches;
+    int rc = (int)cudaGetLastError();
+    if (rc) return rc;
+  }
+  dim3 grid((ncols + 3) / 4, a->n_seg, a->n_poses);
+  if (a->filter == FSB_FILTER_BILINEAR)
+    fsb_colour_kernel<true><<<grid, 128, 0, s>>>(*a);
+  else
+    fsb_colour_kernel<false><<<grid, 128, 0, s>>>(*a);
+  if (launches) ++*launches;
+  return (int)cudaGetLastError();
+}
