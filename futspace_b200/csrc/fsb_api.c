@@ -20,18 +20,32 @@
 #define FSB_MAX_NZ (1 << 22)
 #define FSB_MAX_POSES_PER_LAUNCH 32768
 
+/* Per-launch-group device scratch.  A context owns two sets so that the expand kernel of one launch group (DRAM-bound,
+ * on its own stream) can overlap the march of the next (issue-bound); everything else uses set 0 only. */
+typedef struct fsb_scratch {
+  fsb_frame_consts *fc_dev, *fc_host;
+  int fc_cap;
+  cudaEvent_t fc_free;            /* pinned pose-constant staging may be rewritten */
+  cudaEvent_t coloured, expanded; /* overlap mode: records complete / scratch set free again */
+  int busy;                       /* an expand of this set is in flight on the expand stream */
+  float *table;                   /* per-pose depth tables (blocked by chunk, fsb_kernels.cu) */
+  size_t tab_cap;                 /* floats */
+  void *recs;                     /* march -> expand record lists */
+  uint32_t *sidx;
+  size_t recs_cap, sidx_cap;      /* bytes */
+  uint32_t *cand, *cand_cnt;      /* column-parallel march: candidate lists, their lengths, merge results */
+  uint4_fsb *seg_info;
+  size_t cand_cap, cand_cnt_cap, seg_info_cap; /* bytes */
+} fsb_scratch;
+
 struct fsb_context {
   int device;
-  cudaStream_t stream, copy_stream;
-  cudaEvent_t fc_free;            /* pinned pose-constant staging may be rewritten */
+  cudaStream_t stream, copy_stream, expand_stream;
+  fsb_scratch sc[2];
   cudaEvent_t rendered[2], copied[2];
   char err[512];
   int64_t launches;
   int max_smem_optin, sm_count;
-  fsb_frame_consts *fc_dev, *fc_host;
-  int fc_cap;
-  float *table;                   /* per-pose depth tables (blocked by chunk, fsb_kernels.cu) */
-  size_t tab_cap;                 /* floats */
   uint32_t *frame_dev[2];
   size_t frame_cap[2];            /* pixels */
   int profiling;
@@ -40,13 +54,8 @@ struct fsb_context {
   int64_t prof_n[4];
   int prof_pending;
   unsigned long long *stats_dev;  /* profiling counters: chunks evaluated, records emitted */
-  void *recs;                     /* march -> expand record lists */
   int force_rec8;                 /* env FSB_REC8: always 8-byte records */
-  uint32_t *sidx;
-  size_t recs_cap, sidx_cap;      /* bytes */
-  uint32_t *cand, *cand_cnt;      /* column-parallel march: candidate lists, their lengths, merge results */
-  uint4_fsb *seg_info;
-  size_t cand_cap, cand_cnt_cap, seg_info_cap; /* bytes */
+  int overlap_poses;              /* env FSB_OVERLAP: poses per launch group when expand overlaps the next march (0: off) */
   const float *lut;               /* device address of the colour look-up table */
   int force_march_z;              /* env FSB_MARCH_Z: always the lanes-over-depth march */
   char name[128];
@@ -185,24 +194,32 @@ int fsb_context_new(int device, fsb_context **out) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->fc_free, cudaEventDisableTiming) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&ctx->expand_stream, cudaStreamNonBlocking) != cudaSuccess) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->expand_stream) cudaStreamDestroy(ctx->expand_stream);
     free(ctx);
     return FSB_ERR_CUDA;
   }
   /* the march's colour table lives in the module's global memory of this device; (re)filling it with the same
    * values is harmless, and everything this context launches is ordered after it on ctx->stream */
   if (fsb_launch_lut_init(ctx->stream) != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-    cudaEventDestroy(ctx->fc_free);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->expand_stream);
     free(ctx);
     return FSB_ERR_CUDA;
   }
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&ctx->rendered[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->copied[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->sc[i].fc_free, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->sc[i].coloured, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->sc[i].expanded, cudaEventDisableTiming);
+  }
+  {
+    const char *e = getenv("FSB_OVERLAP");
+    ctx->overlap_poses = e ? atoi(e) : 0;
   }
   ctx->lut = fsb_lut_device_address();
   *out = ctx;
@@ -214,18 +231,24 @@ void fsb_context_free(fsb_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
-  cudaFree(ctx->fc_dev);
-  cudaFreeHost(ctx->fc_host);
-  cudaFree(ctx->table);
+  cudaStreamSynchronize(ctx->expand_stream);
+  for (int i = 0; i < 2; ++i) {
+    fsb_scratch *sc = &ctx->sc[i];
+    cudaFree(sc->fc_dev);
+    cudaFreeHost(sc->fc_host);
+    cudaFree(sc->table);
+    cudaFree(sc->recs);
+    cudaFree(sc->sidx);
+    cudaFree(sc->cand);
+    cudaFree(sc->cand_cnt);
+    cudaFree(sc->seg_info);
+    cudaEventDestroy(sc->fc_free);
+    cudaEventDestroy(sc->coloured);
+    cudaEventDestroy(sc->expanded);
+  }
   cudaFree(ctx->frame_dev[0]);
   cudaFree(ctx->frame_dev[1]);
-  cudaFree(ctx->recs);
-  cudaFree(ctx->sidx);
-  cudaFree(ctx->cand);
-  cudaFree(ctx->cand_cnt);
-  cudaFree(ctx->seg_info);
   cudaFree(ctx->stats_dev);
-  cudaEventDestroy(ctx->fc_free);
   for (int i = 0; i < 5; ++i)
     if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
   for (int i = 0; i < 2; ++i) {
@@ -234,6 +257,7 @@ void fsb_context_free(fsb_context *ctx) {
   }
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
+  cudaStreamDestroy(ctx->expand_stream);
   free(ctx);
 }
 
@@ -243,6 +267,7 @@ int fsb_context_sync(fsb_context *ctx) {
   if (!ctx) return FSB_ERR_ARG;
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->expand_stream));
   return FSB_OK;
 }
 
@@ -429,22 +454,24 @@ void fsb_sun_vector(float sun_height, float sun_ang, float out[3]) {
 int fsb_map_is_packed(const fsb_map *m) { return m && (m->packed != NULL || m->tex != 0); }
 
 /* ------------------------------------------------------------------------------------------ */
-static int ensure_tables(fsb_context *ctx, int n_poses, int tab_stride) {
-  if (n_poses > ctx->fc_cap) {
-    cudaFree(ctx->fc_dev);
-    cudaFreeHost(ctx->fc_host);
-    ctx->fc_dev = NULL; ctx->fc_host = NULL; ctx->fc_cap = 0;
-    CU(ctx, cudaMalloc((void **)&ctx->fc_dev, sizeof(fsb_frame_consts) * (size_t)n_poses));
-    CU(ctx, cudaMallocHost((void **)&ctx->fc_host, sizeof(fsb_frame_consts) * (size_t)n_poses));
-    ctx->fc_cap = n_poses;
+static int ensure_tables(fsb_context *ctx, fsb_scratch *sc, int n_poses, int tab_stride) {
+  if (n_poses > sc->fc_cap) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->expand_stream));
+    cudaFree(sc->fc_dev);
+    cudaFreeHost(sc->fc_host);
+    sc->fc_dev = NULL; sc->fc_host = NULL; sc->fc_cap = 0;
+    CU(ctx, cudaMalloc((void **)&sc->fc_dev, sizeof(fsb_frame_consts) * (size_t)n_poses));
+    CU(ctx, cudaMallocHost((void **)&sc->fc_host, sizeof(fsb_frame_consts) * (size_t)n_poses));
+    sc->fc_cap = n_poses;
   }
   const size_t need = (size_t)n_poses * (size_t)tab_stride;
-  if (need > ctx->tab_cap) {
+  if (need > sc->tab_cap) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->table);
-    ctx->table = NULL; ctx->tab_cap = 0;
-    CU(ctx, cudaMalloc((void **)&ctx->table, need * 4));
-    ctx->tab_cap = need;
+    cudaFree(sc->table);
+    sc->table = NULL; sc->tab_cap = 0;
+    CU(ctx, cudaMalloc((void **)&sc->table, need * 4));
+    sc->tab_cap = need;
   }
   return FSB_OK;
 }
@@ -458,6 +485,7 @@ static int ensure_tables(fsb_context *ctx, int n_poses, int tab_stride) {
 static int grow(fsb_context *ctx, void **ptr, size_t *cap, size_t need) {
   if (need <= *cap) return FSB_OK;
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->expand_stream));
   cudaFree(*ptr);
   *ptr = NULL;
   *cap = 0;
@@ -476,17 +504,17 @@ typedef struct {
   int ncols_pad;
 } render_plan;
 
-static int ensure_scratch(fsb_context *ctx, int n_poses, int ncols, int h, const render_plan *pl) {
+static int ensure_scratch(fsb_context *ctx, fsb_scratch *sc, int n_poses, int ncols, int h, const render_plan *pl) {
   const int n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
   const size_t np = (size_t)n_poses;
   int rc;
-  if ((rc = grow(ctx, &ctx->recs, &ctx->recs_cap, np * ncols * (h + 1) * (pl->rec4 ? 4 : 8)))) return rc;
-  if ((rc = grow(ctx, (void **)&ctx->sidx, &ctx->sidx_cap, np * ncols * (n_bands + 1) * 4))) return rc;
+  if ((rc = grow(ctx, &sc->recs, &sc->recs_cap, np * ncols * (h + 1) * (pl->rec4 ? 4 : 8)))) return rc;
+  if ((rc = grow(ctx, (void **)&sc->sidx, &sc->sidx_cap, np * ncols * (n_bands + 1) * 4))) return rc;
   if (pl->cols) {
     const size_t lists = np * pl->n_seg * pl->ncols_pad;
-    if ((rc = grow(ctx, (void **)&ctx->cand, &ctx->cand_cap, lists * pl->cand_cap * 4))) return rc;
-    if ((rc = grow(ctx, (void **)&ctx->cand_cnt, &ctx->cand_cnt_cap, lists * 4))) return rc;
-    if (pl->n_seg > 1 && (rc = grow(ctx, (void **)&ctx->seg_info, &ctx->seg_info_cap, lists * 16))) return rc;
+    if ((rc = grow(ctx, (void **)&sc->cand, &sc->cand_cap, lists * pl->cand_cap * 4))) return rc;
+    if ((rc = grow(ctx, (void **)&sc->cand_cnt, &sc->cand_cnt_cap, lists * 4))) return rc;
+    if (pl->n_seg > 1 && (rc = grow(ctx, (void **)&sc->seg_info, &sc->seg_info_cap, lists * 16))) return rc;
   }
   return FSB_OK;
 }
@@ -569,10 +597,13 @@ int fsb_context_get_profile(fsb_context *ctx, double *ms, int64_t *launches) {
   return FSB_OK;
 }
 
-/* Queue set-up + render kernels for n poses (n <= FSB_MAX_POSES_PER_LAUNCH) on ctx->stream. */
-static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm, const fsb_map *map,
-                        int h, int w, int col_begin, int col_end, uint32_t *out_dev, int64_t row_stride,
-                        int64_t pose_stride) {
+/* Queue set-up + render kernels for n poses (n <= FSB_MAX_POSES_PER_LAUNCH) on ctx->stream, using scratch set `set`.
+ * overlap != 0: the expand kernel goes to ctx->expand_stream (ordered after the colour pass by an event) so that the
+ * caller can queue the next group's march behind this group's colour pass; the caller joins the streams at the end. */
+static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_camera *cams, int n, const fsb_params *prm,
+                           const fsb_map *map, int h, int w, int col_begin, int col_end, uint32_t *out_dev,
+                           int64_t row_stride, int64_t pose_stride) {
+  fsb_scratch *sc = &ctx->sc[set];
   fsb_frame_consts single;
   int max_nz = 0;
   if (row_stride > (int64_t)(INT32_MAX / 4)) /* fsb_expand_kernel forms row offsets from a 32-bit byte stride */
@@ -585,13 +616,13 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   }
   int rc;
   if (n > 1) {
-    if ((rc = ensure_tables(ctx, n, 160 * 6))) return rc;
-    CU(ctx, cudaEventSynchronize(ctx->fc_free));
+    if ((rc = ensure_tables(ctx, sc, n, 160 * 6))) return rc;
+    CU(ctx, cudaEventSynchronize(sc->fc_free));
     for (int i = 0; i < n; ++i) {
-      if (make_consts(&cams[i], prm, map, w, &ctx->fc_host[i]))
+      if (make_consts(&cams[i], prm, map, w, &sc->fc_host[i]))
         return set_err(ctx, FSB_ERR_RANGE, "render: z-series undefined for pose %d (distance=%g)", i,
                        (double)cams[i].distance);
-      if (ctx->fc_host[i].n_z > max_nz) max_nz = ctx->fc_host[i].n_z;
+      if (sc->fc_host[i].n_z > max_nz) max_nz = sc->fc_host[i].n_z;
     }
   }
   if (prm->flags & FSB_FLAG_SMOOTHING) {
@@ -603,7 +634,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   /* depth table: one 160-float block per chunk of 32 samples, plus the blocks the march loop prefetches
    * past the last chunk (fsb_kernels.cu) */
   const int tab_stride = 160 * ((max_nz + 31) / 32 + 6);
-  if ((rc = ensure_tables(ctx, n, tab_stride))) return rc;
+  if ((rc = ensure_tables(ctx, sc, n, tab_stride))) return rc;
   /* ---- plan: which march, which record format, how the depth series is split ---- */
   render_plan pl;
   memset(&pl, 0, sizeof pl);
@@ -650,18 +681,22 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     pl.cand_cap = seg_steps < h ? seg_steps : h;
     if (pl.cand_cap < 1) pl.cand_cap = 1;
   }
-  if ((rc = ensure_scratch(ctx, n, ncols, h, &pl))) return rc;
+  if ((rc = ensure_scratch(ctx, sc, n, ncols, h, &pl))) return rc;
+  if (sc->busy) { /* an earlier group's expand still reads this scratch set (and its pose constants) */
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, sc->expanded, 0));
+    sc->busy = 0;
+  }
   if (n > 1) {
-    CU(ctx, cudaMemcpyAsync(ctx->fc_dev, ctx->fc_host, sizeof(fsb_frame_consts) * (size_t)n, cudaMemcpyHostToDevice,
+    CU(ctx, cudaMemcpyAsync(sc->fc_dev, sc->fc_host, sizeof(fsb_frame_consts) * (size_t)n, cudaMemcpyHostToDevice,
                             ctx->stream));
-    CU(ctx, cudaEventRecord(ctx->fc_free, ctx->stream));
+    CU(ctx, cudaEventRecord(sc->fc_free, ctx->stream));
   }
   if (ctx->profiling) {
     int prc = prof_collect(ctx);
     if (prc) return prc;
     CU(ctx, cudaEventRecord(ctx->pev[0], ctx->stream));
   }
-  CU(ctx, (cudaError_t)fsb_launch_setup(ctx->fc_dev, n == 1 ? &single : NULL, n, ctx->table, tab_stride,
+  CU(ctx, (cudaError_t)fsb_launch_setup(sc->fc_dev, n == 1 ? &single : NULL, n, sc->table, tab_stride,
                                         ctx->stream, &ctx->launches));
   if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[1], ctx->stream));
   fsb_render_args a;
@@ -671,8 +706,8 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.height = map->height;
   a.q = map->q;
   a.r = map->r;
-  a.fc = ctx->fc_dev;
-  a.table = ctx->table;
+  a.fc = sc->fc_dev;
+  a.table = sc->table;
   a.tab_stride = tab_stride;
   a.xmask_hi = (map->r - 1) & ~7;
   a.ymask_hi = (map->q - 1) & ~3;
@@ -689,8 +724,8 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.f2i_mode = prm->f2i_mode;
   a.alpha_bits = map->alpha_bits;
   a.stats = ctx->profiling ? ctx->stats_dev : NULL;
-  a.recs = (uint2_fsb *)ctx->recs;
-  a.sidx = ctx->sidx;
+  a.recs = (uint2_fsb *)sc->recs;
+  a.sidx = sc->sidx;
   a.rec_cap = h + 1; /* + the guard record */
   a.rb_shift = FSB_RB_SHIFT;
   a.smooth = smooth;
@@ -703,9 +738,9 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.rec4 = pl.rec4;
   a.full_eval = (prm->flags & FSB_FLAG_NO_CULL) ? 1 : 0;
   a.lut = ctx->lut;
-  a.cand = ctx->cand;
-  a.cand_cnt = ctx->cand_cnt;
-  a.seg_info = ctx->seg_info;
+  a.cand = sc->cand;
+  a.cand_cnt = sc->cand_cnt;
+  a.seg_info = sc->seg_info;
   a.n_seg = pl.n_seg;
   a.cand_cap = pl.cand_cap;
   a.ncols_pad = pl.ncols_pad;
@@ -719,11 +754,35 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
   }
   if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[3], ctx->stream));
-  CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));
+  if (overlap) {
+    CU(ctx, cudaEventRecord(sc->coloured, ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->expand_stream, sc->coloured, 0));
+    CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->expand_stream, &ctx->launches));
+    CU(ctx, cudaEventRecord(sc->expanded, ctx->expand_stream));
+    sc->busy = 1;
+  } else {
+    CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));
+  }
   if (ctx->profiling) {
     CU(ctx, cudaEventRecord(ctx->pev[4], ctx->stream));
     ctx->prof_pending = 1;
   }
+  return FSB_OK;
+}
+
+static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm, const fsb_map *map,
+                        int h, int w, int col_begin, int col_end, uint32_t *out_dev, int64_t row_stride,
+                        int64_t pose_stride) {
+  return render_poses_on(ctx, 0, 0, cams, n, prm, map, h, w, col_begin, col_end, out_dev, row_stride, pose_stride);
+}
+
+/* every expand still in flight on the expand stream becomes a dependency of ctx->stream */
+static int join_expand_stream(fsb_context *ctx) {
+  for (int i = 0; i < 2; ++i)
+    if (ctx->sc[i].busy) {
+      CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->sc[i].expanded, 0));
+      ctx->sc[i].busy = 0;
+    }
   return FSB_OK;
 }
 
@@ -749,12 +808,21 @@ int fsb_render_batch_device(fsb_context *ctx, const fsb_camera *cams, int n, con
   if (rc) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   const int64_t frame = (int64_t)h * w;
-  const int g = group_size(n, w, h);
-  for (int i = 0; i < n; i += g) {
+  int g = group_size(n, w, h);
+  /* Overlap mode: launch groups of `overlap_poses` alternate between the two scratch sets; the expand of a group (DRAM-
+   * bound frame stores) runs on the expand stream beside the march + colour pass of the next group (issue-bound). */
+  const int ov = ctx->overlap_poses > 0 && !ctx->profiling && n >= 2 * ctx->overlap_poses;
+  if (ov && ctx->overlap_poses < g) g = ctx->overlap_poses;
+  int it = 0;
+  for (int i = 0; i < n; i += g, ++it) {
     int c = n - i < g ? n - i : g;
-    if ((rc = render_poses(ctx, cams + i, c, prm, map, h, w, 0, w, out_dev + (size_t)i * frame, w, frame))) return rc;
+    if ((rc = render_poses_on(ctx, ov ? (it & 1) : 0, ov, cams + i, c, prm, map, h, w, 0, w, out_dev + (size_t)i * frame, w,
+                              frame))) {
+      join_expand_stream(ctx);
+      return rc;
+    }
   }
-  return FSB_OK;
+  return join_expand_stream(ctx);
 }
 
 static int ensure_frame(fsb_context *ctx, int slot, size_t pixels) {

@@ -101,29 +101,40 @@ __device__ __forceinline__ void cstep_resolve(const col_step<BIL> &t, float iz, 
   }
 }
 
-/* U = depth steps per register set; two sets are in flight (the gathers of one are issued before the other is resolved). */
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+/* U = depth steps per register set; two sets are in flight (the gathers of one are issued before the other is resolved).
+ *
+ * Depth table: the 640-byte block of a chunk of 32 steps ({sx,sy,dx,dy} x 32, inv_z x 32) is the same for every column, so
+ * the CTA (4 warps = 128 adjacent columns of one pose and depth segment) stages it in shared memory with cp.async, two
+ * blocks ahead of the one being marched: the per-step operands are LDS broadcasts (29 cycles) instead of global loads
+ * queued behind the texture gathers in the same L1 pipe (round-2 ncu: the largest stall site of the first version). */
 template <bool BIL, int U, int MINB>
 __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(const fsb_render_args a) {
   static_assert(32 % (2 * U) == 0, "a pair of register sets must tile a 32-step table block");
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ __align__(16) float sm[3][FSB_TAB_BLOCK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pose = blockIdx.z, seg = blockIdx.y;
   const int ncols = a.col_end - a.col_begin;
   const int jrel = (blockIdx.x * FSB_MC_WARPS + warp) * 32 + lane;
-  if (jrel - lane >= ncols) return;
-  /* lanes past the last column of a ragged group march a column of their own into the padding of the scratch lists
-   * (ncols_pad): no masking in the loop, and nobody reads those lists */
+  /* a warp with no column stays in the loop for the barriers; lanes past the last column of a ragged group march a
+   * column of their own into the padding of the scratch lists (ncols_pad): no masking in the loop, nobody reads them */
+  bool active = jrel - lane < ncols;
   const fsb_frame_consts *fcp = a.fc + pose;
   const float cam_h = fcp->cam_h, horizon = fcp->horizon, cull_d = fcp->cull_d;
   const int n_chunks = (fcp->n_z + 31) >> 5;
   const float *tab = a.table + (size_t)pose * a.tab_stride;
-  const size_t lid = ((size_t)pose * a.n_seg + seg) * a.ncols_pad + jrel;
+  const size_t lid = ((size_t)pose * a.n_seg + seg) * a.ncols_pad + (active ? jrel : 0);
   col_state st;
   st.ybuf_f = (float)a.h;
   st.list = a.cand + lid * a.cand_cap;
   st.n = 0;
   const float fj = (float)(a.col_begin + jrel);
 
-  /* this warp's share of the depth series, in table blocks of 32 samples */
+  /* this CTA's share of the depth series, in table blocks of 32 samples */
   int c_first = (int)(((long long)n_chunks * seg) / a.n_seg);
   const int c_end = (int)(((long long)n_chunks * (seg + 1)) / a.n_seg);
   /* Occlusion bound (see fsb_kernels.cu): camera above the highest terrain -> a prefix of the series projects below the
@@ -146,45 +157,59 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
   const bool can_stop = cull_d < 0.0f && cull_d > -INFINITY;
   int c_done = 0;
   if (c_first < c_end) {
+    /* blocks c_first and c_first + 1 (the table is padded with blocks that repeat the last sample) */
+    const float *gsrc = tab + (size_t)c_first * FSB_TAB_BLOCK + tid * 4;
+    if (tid < FSB_TAB_BLOCK / 4) {
+      cp_async16(&sm[0][tid * 4], gsrc);
+      cp_async16(&sm[1][tid * 4], gsrc + FSB_TAB_BLOCK);
+    }
+    cp_async_wait_all();
+    __syncthreads();
     col_step<BIL> sa[U], sb[U];
-    const float4 *bl = reinterpret_cast<const float4 *>(tab + (size_t)c_first * FSB_TAB_BLOCK);
-    asm volatile("" : "+l"(bl));
+    if (active) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, __ldg(bl + u), fj);
+      for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, reinterpret_cast<const float4 *>(sm[0])[u], fj);
+    }
+    int slot = 0;
     for (int c = c_first; c < c_end; ++c) {
-      const float *bz = reinterpret_cast<const float *>(bl) + 128; /* the block's 32 inv_z (:217) */
-      if (!a.full_eval) {
+      const int slot1 = slot == 2 ? 0 : slot + 1, slot2 = slot1 == 2 ? 0 : slot1 + 1;
+      /* block c + 2 -> the slot block c - 1 was read from (every warp has passed the barrier that ended it) */
+      if (tid < FSB_TAB_BLOCK / 4) cp_async16(&sm[slot2][tid * 4], gsrc + (size_t)(c - c_first + 2) * FSB_TAB_BLOCK);
+      const float4 *tl = reinterpret_cast<const float4 *>(sm[slot]);
+      const float *tz = sm[slot] + 128; /* the block's 32 inv_z (:217) */
+      if (active && !a.full_eval) {
         float bound = 0.0f;
-        if (can_stop) bound = (float)max(0, __float2int_rz(__fadd_rn(__fmul_rn(cull_d, __ldg(bz)), horizon)));
-        if (!__any_sync(FSB_FULL, st.ybuf_f > bound)) break; /* every column of the group is finished */
+        if (can_stop) bound = (float)max(0, __float2int_rz(__fadd_rn(__fmul_rn(cull_d, tz[0]), horizon)));
+        active = __any_sync(FSB_FULL, st.ybuf_f > bound); /* false: every column of the group is finished, for good */
       }
-      ++c_done;
-      const uint32_t kw = (uint32_t)(c << 5) << FSB_ROW_BITS;
+      if (active) {
+        ++c_done;
+        const float4 *tl_next = reinterpret_cast<const float4 *>(sm[slot1]);
+        uint32_t kw = (uint32_t)(c << 5) << FSB_ROW_BITS;
+#pragma unroll 1
+        for (int i = 0; i < 32; i += 2 * U, kw += (uint32_t)(2 * U) << FSB_ROW_BITS) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 2 * U) {
+          for (int u = 0; u < U; ++u) cstep_issue<BIL>(sb[u], a, tl[i + U + u], fj);
 #pragma unroll
-        for (int u = 0; u < U; ++u) cstep_issue<BIL>(sb[u], a, __ldg(bl + i + U + u), fj);
+          for (int u = 0; u < U; ++u)
+            cstep_resolve<BIL>(sa[u], tz[i + u], cam_h, horizon, kw + ((uint32_t)u << FSB_ROW_BITS), st);
+          /* next set: the following steps of this block, or the head of the next block (a repeated last sample in the
+           * padding projects to the same row and `occlude` keeps the earlier one) */
+          const float4 *nx = i + 2 * U < 32 ? tl + i + 2 * U : tl_next;
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-          cstep_resolve<BIL>(sa[u], __ldg(bz + i + u), cam_h, horizon, kw + ((uint32_t)(i + u) << FSB_ROW_BITS), st);
-        /* next set: the following steps of this block, or the head of the next block (the table is padded with
-         * blocks that repeat the last sample: a repeated sample projects to the same row and `occlude` keeps the
-         * earlier one) */
+          for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, nx[u], fj);
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-          cstep_issue<BIL>(sa[u], a, __ldg(bl + (i + 2 * U < 32 ? i + 2 * U + u : FSB_TAB_BLOCK / 4 + u)), fj);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          cstep_resolve<BIL>(sb[u], __ldg(bz + i + U + u), cam_h, horizon, kw + ((uint32_t)(i + U + u) << FSB_ROW_BITS), st);
+          for (int u = 0; u < U; ++u)
+            cstep_resolve<BIL>(sb[u], tz[i + U + u], cam_h, horizon, kw + ((uint32_t)(U + u) << FSB_ROW_BITS), st);
+        }
       }
-      bl += FSB_TAB_BLOCK / 4;
-      /* the block pointer is warp-uniform; kept in a vector register pair (opaque to the compiler) the 40 loads of a
-       * block address it as [R + imm] instead of copying a uniform register pair in front of every load */
-      asm volatile("" : "+l"(bl));
+      cp_async_wait_all();
+      if (!__syncthreads_or(active)) break; /* block c + 2 visible; everyone is done with block c */
+      slot = slot1;
     }
   }
-  a.cand_cnt[lid] = (uint32_t)st.n;
-  if (a.stats) {
+  if (jrel - lane < ncols) a.cand_cnt[lid] = (uint32_t)st.n;
+  if (a.stats && jrel - lane < ncols) {
     /* in chunks of 32 samples of one column, like the lanes-over-depth march counts them */
     if (lane == 0) atomicAdd(a.stats, (unsigned long long)c_done * (unsigned long long)min(32, ncols - (jrel - lane)));
     const unsigned long long n = (jrel < ncols) ? (unsigned long long)st.n : 0ull;
@@ -244,7 +269,49 @@ __global__ void __launch_bounds__(128) fsb_merge_kernel(const fsb_render_args a)
 /* ------------------------------------------------------------------------------------------ */
 /* Colour: one warp per (pose, column[, segment]), lane = record.  Reads the sample index, rebuilds the sample position
  * (get_segment, :63-66), runs png_color / png_color_filtered and writes the record the expand kernels consume, plus the
- * per-band index of the list (sidx[b] = number of records with row >= b * 32; rows strictly decrease along the list). */
+ * per-band index of the list (sidx[b] = number of records with row >= b * 32; rows strictly decrease along the list).
+ *
+ * The bilinear filter is the unit-weight, alpha 0x00/0xFF form of fsb_device.cuh (sample_color) spelled for this pass:
+ *   - ceil x = floor x + (x > floor x), as in the march: two FRND instead of four;
+ *   - u32.f32 (v * 255) for v * 255 in [0, 256) is the low byte of round-toward-zero (v * 255 + 2^23): an FADD.RZ on the
+ *     FP32 pipe instead of an F2I on the quarter-rate XU pipe, which the nine square roots of a sample already load.
+ * Anything else (integer coordinate, |coordinate| < 1, other alpha) takes sample_color unchanged. */
+__device__ __forceinline__ uint32_t byte_bits(float v) { /* 0x4B0000nn with nn = u32.f32 (v * 255), 0 <= v * 255 < 256 */
+  return __float_as_uint(__fadd_rz(__fmul_rn(v, 255.0f), 8388608.0f));
+}
+__device__ __forceinline__ float mix_unit_sqrt(float m1, float s1, float m2, float s2) {
+  return sqrt_rn_unit(__fadd_rn(__fmul_rn(m1, s1), __fmul_rn(m2, s2)));
+}
+/* one channel of png_color_filtered from the four normalised texels: -> 0x4B0000nn */
+__device__ __forceinline__ uint32_t colour_channel(float v00, float v01, float v10, float v11, float wx0, float wx1, float wy0,
+                                                   float wy1, const float *__restrict__ sq) {
+  const uint32_t i1 = byte_bits(mix_unit_sqrt(wx0, __fmul_rn(v00, v00), wx1, __fmul_rn(v01, v01)));
+  const uint32_t i2 = byte_bits(mix_unit_sqrt(wx0, __fmul_rn(v10, v10), wx1, __fmul_rn(v11, v11)));
+  return byte_bits(mix_unit_sqrt(wy0, sq[i1 & 255u], wy1, sq[i2 & 255u]));
+}
+
+template <bool BIL>
+__device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x, float y, const float *un, const float *sq) {
+  if (!BIL) return sample_color<MEM_TEX, false, FSB_F2I_SATURATE>(a, x, y, un, sq);
+  const float fx = floorf(x), fy = floorf(y);
+  const float wx1 = __fsub_rn(x, fx), wy1 = __fsub_rn(y, fy);
+  const float wx0 = __fsub_rn(__fadd_rn(fx, wx1 > 0.0f ? 1.0f : 0.0f), x), wy0 = __fsub_rn(__fadd_rn(fy, wy1 > 0.0f ? 1.0f : 0.0f), y);
+  const uint32_t al = a.alpha_bits;
+  if ((al == 0xFF000000u || al == 0u) && __fadd_rn(wx0, wx1) == 1.0f && __fadd_rn(wy0, wy1) == 1.0f) {
+    const float u = __fmul_rn(__fadd_rn(fx, 1.0f), a.inv_r), v = __fmul_rn(__fadd_rn(fy, 1.0f), a.inv_q);
+    float r00, r01, r10, r11, g00, g01, g10, g11, b00, b01, b10, b11;
+    FSB_TLD4_F32C("b", a.tex_f, u, v, r10, r11, r01, r00); /* channel order of the RGBA8 texel is {B, G, R, height} */
+    FSB_TLD4_F32C("g", a.tex_f, u, v, g10, g11, g01, g00);
+    FSB_TLD4_F32C("r", a.tex_f, u, v, b10, b11, b01, b00);
+    const uint32_t r = colour_channel(r00, r01, r10, r11, wx0, wx1, wy0, wy1, sq);
+    const uint32_t g = colour_channel(g00, g01, g10, g11, wx0, wx1, wy0, wy1, sq);
+    const uint32_t b = colour_channel(b00, b01, b10, b11, wx0, wx1, wy0, wy1, sq);
+    /* low bytes of b, g, r under the alpha byte */
+    return (__byte_perm(__byte_perm(b, g, 0x0040), r, 0x7410) & 0x00FFFFFFu) | al;
+  }
+  return sample_color<MEM_TEX, true, FSB_F2I_SATURATE>(a, x, y, un, sq);
+}
+
 template <bool BIL>
 __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a) {
   const float *un = a.lut, *sq = a.lut + 256;
@@ -267,34 +334,50 @@ __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a
   }
   const size_t colid = (size_t)pose * ncols + col;
   uint32_t *sidx = a.sidx + colid * (a.n_bands + 1);
-  uint32_t *rec4 = reinterpret_cast<uint32_t *>(a.recs) + colid * a.rec_cap + 1;
-  uint2 *rec8 = a.recs + colid * a.rec_cap + 1;
+  uint32_t *rec4 = reinterpret_cast<uint32_t *>(a.recs) + colid * a.rec_cap + 1 + off;
+  uint2 *rec8 = a.recs + colid * a.rec_cap + 1 + off;
   if (seg == 0 && lane == 0) { /* slot 0: the guard record the 8-byte walks stop at (see fsb_kernels.cu) */
     if (a.rec4) rec4[-1] = 0u;
     else rec8[-1] = make_uint2(0xffffffffu, 0u);
   }
   const float *tab = a.table + (size_t)pose * a.tab_stride;
   const float fj = (float)(a.col_begin + col);
+  /* the candidate word and the depth-table entry of the next 32 records are fetched while this chunk is filtered */
+  uint32_t word_n = 0;
+  float4 l_n = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < n) {
+    word_n = src[lane];
+    const uint32_t k = word_n >> FSB_ROW_BITS;
+    l_n = __ldg(reinterpret_cast<const float4 *>(tab + (k >> 5) * FSB_TAB_BLOCK) + (k & 31));
+  }
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
     const bool valid = i < n;
-    uint32_t word = 0, colour = 0;
+    const uint32_t word = word_n;
+    const float4 l = l_n;
+    if (i + 32 < n) {
+      word_n = src[i + 32];
+      const uint32_t k = word_n >> FSB_ROW_BITS;
+      l_n = __ldg(reinterpret_cast<const float4 *>(tab + (k >> 5) * FSB_TAB_BLOCK) + (k & 31));
+    }
+    const uint32_t row = word & FSB_ROW_MASK;
     if (valid) {
-      word = src[i];
-      const uint32_t k = word >> FSB_ROW_BITS;
-      const float4 l = __ldg(reinterpret_cast<const float4 *>(tab + (size_t)(k >> 5) * FSB_TAB_BLOCK) + (k & 31));
       const float x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
       const float y = __fadd_rn(l.y, __fmul_rn(fj, l.w));
-      colour = sample_color<MEM_TEX, BIL, FSB_F2I_SATURATE>(a, x, y, un, sq);
-      const uint32_t row = word & FSB_ROW_MASK;
-      if (a.rec4) rec4[off + i] = (colour & 0x80FFFFFFu) | ((row & 31u) << 24);
-      else rec8[off + i] = make_uint2(a.smooth ? word : row, colour);
+      const uint32_t colour = colour_of<BIL>(a, x, y, un, sq);
+      if (a.rec4) rec4[i] = (colour & 0x80FFFFFFu) | ((row & 31u) << 24);
+      else rec8[i] = make_uint2(a.smooth ? word : row, colour);
     }
-    const int band = (int)((word & FSB_ROW_MASK) >> a.rb_shift);
+    /* band index: the record that opens a new band writes the list position for every band it skipped */
+    const int band = (int)(row >> a.rb_shift);
     int pb = __shfl_up_sync(FSB_FULL, band, 1);
     if (lane == 0) pb = prev_band;
-    if (valid)
-      for (int b = band + 1; b <= pb; ++b) sidx[b] = (uint32_t)(off + i);
+    if (valid && band < pb) {
+      int b = pb;
+#pragma unroll 1
+      do sidx[b] = (uint32_t)(off + i);
+      while (--b > band);
+    }
     prev_band = __shfl_sync(FSB_FULL, band, min(n - base, 32) - 1);
   }
   /* unsplit series: bands at or above the last record */
