@@ -508,8 +508,9 @@ static int ensure_scratch(fsb_context *ctx, fsb_scratch *sc, int n_poses, int nc
   const int n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
   const size_t np = (size_t)n_poses;
   int rc;
-  if ((rc = grow(ctx, &sc->recs, &sc->recs_cap, np * ncols * (h + 1) * (pl->rec4 ? 4 : 8)))) return rc;
-  if ((rc = grow(ctx, (void **)&sc->sidx, &sc->sidx_cap, np * ncols * (n_bands + 1) * 4))) return rc;
+  const size_t lc = pl->cols ? (size_t)pl->ncols_pad : (size_t)ncols; /* lists: interleaved by groups of 32 columns, or one per column */
+  if ((rc = grow(ctx, &sc->recs, &sc->recs_cap, np * lc * (h + 1) * (pl->rec4 ? 4 : 8)))) return rc;
+  if ((rc = grow(ctx, (void **)&sc->sidx, &sc->sidx_cap, np * lc * (n_bands + 1) * 4))) return rc;
   if (pl->cols) {
     const size_t lists = np * pl->n_seg * pl->ncols_pad;
     if ((rc = grow(ctx, (void **)&sc->cand, &sc->cand_cap, lists * pl->cand_cap * 4))) return rc;
@@ -727,6 +728,7 @@ static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_cam
   a.recs = (uint2_fsb *)sc->recs;
   a.sidx = sc->sidx;
   a.rec_cap = h + 1; /* + the guard record */
+  a.rec_stride = pl.cols ? 32 : 1;
   a.rb_shift = FSB_RB_SHIFT;
   a.smooth = smooth;
   a.n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;

@@ -45,8 +45,8 @@ typedef struct fsb_render_args {
   const int32_t *height;    /* [q][r]       */
   int32_t q, r;
   const fsb_frame_consts *fc; /* device, [n_poses] */
-  const float *table;       /* device, [n_poses][tab_stride]: per chunk of 32 depth samples a 640-byte block     */
-  int32_t tab_stride;       /* floats per pose = 160 * (n_chunks + 6): the march prefetches past the last chunk */
+  const float *table;       /* device, [n_poses][tab_stride]: per pose kcap x {sx,sy,dx,dy}, then kcap x inv_z    */
+  int32_t tab_stride;       /* floats per pose = 5 * kcap, kcap = 32 * (n_chunks + 6): the march prefetches past the last chunk */
   uint32_t *out;            /* device; pixel (pose 0, row 0, column col_begin)              */
   int64_t row_stride;       /* pixels */
   int64_t pose_stride;      /* pixels */
@@ -58,7 +58,8 @@ typedef struct fsb_render_args {
   /* march -> expand hand-off (device scratch, L2-resident in steady state) */
   uint2_fsb *recs;          /* [n_poses][ncols][rec_cap] {row, colour}: visible samples front to back  */
   uint32_t *sidx;           /* [n_poses][ncols][n_bands+1]: sidx[b] = #records with row >= b<<rb_shift */
-  int32_t rec_cap;          /* = h (rows strictly decrease along a list)                               */
+  int32_t rec_cap;          /* = h + 1: the guard slot, then at most h records (rows strictly decrease along a list) */
+  int32_t rec_stride;       /* 1: a contiguous list per column; 32: lists of 32 adjacent columns interleaved (fsb_kernels.cu list_view) */
   int32_t n_bands, rb_shift;
   int32_t rec4;             /* 1: 4-byte records (row & 31) << 24 | alpha flag << 31 | rgb (packed maps, alpha 0x00 / 0xFF) */
   int32_t smooth;           /* smoothing #on: record .x = row | sample index << 15 (fsb_expand_smooth_kernel) */

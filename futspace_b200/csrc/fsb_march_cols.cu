@@ -78,7 +78,7 @@ __device__ __forceinline__ float cstep_height(const col_step<BIL> &t) {
  * always, :225, so nothing can pass `y < 0` any more) and the append pointer of the column's candidate list. */
 struct col_state {
   float ybuf_f;
-  uint32_t *list;
+  uint32_t *list; /* entry p of this lane's column at list[p * 32] */
   int n;
 };
 
@@ -95,7 +95,8 @@ __device__ __forceinline__ void cstep_resolve(const col_step<BIL> &t, float iz, 
     const int yy = max(0, __float2int_rz(rel));
     const float yf = (float)yy;
     if (cand && yf < st.ybuf_f) {
-      st.list[st.n++] = (uint32_t)yy | kword;
+      st.list[(size_t)st.n * 32] = (uint32_t)yy | kword;
+      ++st.n;
       st.ybuf_f = yy > 0 ? yf : -INFINITY;
     }
   }
@@ -106,35 +107,45 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+/* Scratch layout of this file (and of the expand kernels behind it, list_view in fsb_kernels.cu): the lists of the 32
+ * columns of a group are interleaved -- entry p of lane l at (p * 32 + l) words from the group's base -- because every
+ * kernel here has lane = column: appends of neighbouring columns share 128-byte lines instead of touching 32. */
+__device__ __forceinline__ size_t cand_group_base(const fsb_render_args &a, int pose, int seg, int group) {
+  return (((size_t)pose * a.n_seg + seg) * (a.ncols_pad >> 5) + group) * a.cand_cap * 32;
+}
+
 /* U = depth steps per register set; two sets are in flight (the gathers of one are issued before the other is resolved).
  *
- * Depth table: the 640-byte block of a chunk of 32 steps ({sx,sy,dx,dy} x 32, inv_z x 32) is the same for every column, so
- * the CTA (4 warps = 128 adjacent columns of one pose and depth segment) stages it in shared memory with cp.async, two
- * blocks ahead of the one being marched: the per-step operands are LDS broadcasts (29 cycles) instead of global loads
+ * Depth table: the 640 bytes of a chunk of 32 steps ({sx,sy,dx,dy} x 32, inv_z x 32) are the same for every column, so
+ * the CTA (4 warps = 128 adjacent columns of one pose and depth segment) stages them in shared memory with cp.async, two
+ * chunks ahead of the one being marched: the per-step operands are LDS broadcasts (29 cycles) instead of global loads
  * queued behind the texture gathers in the same L1 pipe (round-2 ncu: the largest stall site of the first version). */
 template <bool BIL, int U, int MINB>
 __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(const fsb_render_args a) {
-  static_assert(32 % (2 * U) == 0, "a pair of register sets must tile a 32-step table block");
+  static_assert(32 % (2 * U) == 0, "a pair of register sets must tile a 32-step chunk");
   __shared__ __align__(16) float sm[3][FSB_TAB_BLOCK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pose = blockIdx.z, seg = blockIdx.y;
   const int ncols = a.col_end - a.col_begin;
-  const int jrel = (blockIdx.x * FSB_MC_WARPS + warp) * 32 + lane;
-  /* a warp with no column stays in the loop for the barriers; lanes past the last column of a ragged group march a
-   * column of their own into the padding of the scratch lists (ncols_pad): no masking in the loop, nobody reads them */
-  bool active = jrel - lane < ncols;
+  const int group = blockIdx.x * FSB_MC_WARPS + warp;
+  const int jrel = group * 32 + lane;
+  /* A warp with no column stays in the loop for the barriers.  Lanes past the last column of a ragged group march a
+   * column of their own into the padding of the scratch lists (ncols_pad): no masking in the loop, nobody reads them.
+   * (`active` only ever holds vote results, so the compiler knows it is warp-uniform.) */
+  bool active = __any_sync(FSB_FULL, group * 32 < ncols);
   const fsb_frame_consts *fcp = a.fc + pose;
   const float cam_h = fcp->cam_h, horizon = fcp->horizon, cull_d = fcp->cull_d;
   const int n_chunks = (fcp->n_z + 31) >> 5;
-  const float *tab = a.table + (size_t)pose * a.tab_stride;
-  const size_t lid = ((size_t)pose * a.n_seg + seg) * a.ncols_pad + (active ? jrel : 0);
+  const int kcap = a.tab_stride / 5;
+  const float4 *line = reinterpret_cast<const float4 *>(a.table + (size_t)pose * a.tab_stride); /* {sx,sy,dx,dy}[k] */
+  const float *invz = a.table + (size_t)pose * a.tab_stride + 4 * (size_t)kcap;                 /* inv_z[k] (:217)  */
   col_state st;
   st.ybuf_f = (float)a.h;
-  st.list = a.cand + lid * a.cand_cap;
+  st.list = a.cand + (active ? cand_group_base(a, pose, seg, group) : 0) + lane;
   st.n = 0;
   const float fj = (float)(a.col_begin + jrel);
 
-  /* this CTA's share of the depth series, in table blocks of 32 samples */
+  /* this CTA's share of the depth series, in chunks of 32 samples */
   int c_first = (int)(((long long)n_chunks * seg) / a.n_seg);
   const int c_end = (int)(((long long)n_chunks * (seg + 1)) / a.n_seg);
   /* Occlusion bound (see fsb_kernels.cu): camera above the highest terrain -> a prefix of the series projects below the
@@ -143,7 +154,7 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
     int first = c_end;
     for (int base = c_first; base < c_end; base += 32) {
       const int ci = min(base + lane, c_end - 1);
-      const float izl = __ldg(tab + (size_t)ci * FSB_TAB_BLOCK + 128 + 31);
+      const float izl = __ldg(invz + ci * 32 + 31);
       const bool below = max(0, __float2int_rz(__fadd_rn(__fmul_rn(cull_d, izl), horizon))) >= a.h;
       const unsigned alive = __ballot_sync(FSB_FULL, !below);
       if (alive) {
@@ -157,12 +168,17 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
   const bool can_stop = cull_d < 0.0f && cull_d > -INFINITY;
   int c_done = 0;
   if (c_first < c_end) {
-    /* blocks c_first and c_first + 1 (the table is padded with blocks that repeat the last sample) */
-    const float *gsrc = tab + (size_t)c_first * FSB_TAB_BLOCK + tid * 4;
-    if (tid < FSB_TAB_BLOCK / 4) {
+    /* staging: threads 0..31 copy one {sx,sy,dx,dy} each, threads 32..39 four inv_z each; chunks c_first and c_first + 1
+     * first (the table is padded with entries that repeat the last sample) */
+    const bool stager = tid < FSB_TAB_BLOCK / 4;
+    const char *gsrc = tid < 32 ? reinterpret_cast<const char *>(line + c_first * 32 + tid)
+                                : reinterpret_cast<const char *>(invz + c_first * 32 + (tid - 32) * 4);
+    const int gstep = tid < 32 ? 32 * 16 : 32 * 4; /* bytes per chunk in the source array */
+    if (stager) {
       cp_async16(&sm[0][tid * 4], gsrc);
-      cp_async16(&sm[1][tid * 4], gsrc + FSB_TAB_BLOCK);
+      cp_async16(&sm[1][tid * 4], gsrc + gstep);
     }
+    gsrc += 2 * gstep;
     cp_async_wait_all();
     __syncthreads();
     col_step<BIL> sa[U], sb[U];
@@ -173,10 +189,11 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
     int slot = 0;
     for (int c = c_first; c < c_end; ++c) {
       const int slot1 = slot == 2 ? 0 : slot + 1, slot2 = slot1 == 2 ? 0 : slot1 + 1;
-      /* block c + 2 -> the slot block c - 1 was read from (every warp has passed the barrier that ended it) */
-      if (tid < FSB_TAB_BLOCK / 4) cp_async16(&sm[slot2][tid * 4], gsrc + (size_t)(c - c_first + 2) * FSB_TAB_BLOCK);
+      /* chunk c + 2 -> the slot chunk c - 1 was read from (every warp has passed the barrier that ended it) */
+      if (stager) cp_async16(&sm[slot2][tid * 4], gsrc);
+      gsrc += gstep;
       const float4 *tl = reinterpret_cast<const float4 *>(sm[slot]);
-      const float *tz = sm[slot] + 128; /* the block's 32 inv_z (:217) */
+      const float *tz = sm[slot] + 128;
       if (active && !a.full_eval) {
         float bound = 0.0f;
         if (can_stop) bound = (float)max(0, __float2int_rz(__fadd_rn(__fmul_rn(cull_d, tz[0]), horizon)));
@@ -185,38 +202,38 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
       if (active) {
         ++c_done;
         const float4 *tl_next = reinterpret_cast<const float4 *>(sm[slot1]);
-        uint32_t kw = (uint32_t)(c << 5) << FSB_ROW_BITS;
-#pragma unroll 1
-        for (int i = 0; i < 32; i += 2 * U, kw += (uint32_t)(2 * U) << FSB_ROW_BITS) {
+        const uint32_t kw = (uint32_t)(c << 5) << FSB_ROW_BITS;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2 * U) {
 #pragma unroll
           for (int u = 0; u < U; ++u) cstep_issue<BIL>(sb[u], a, tl[i + U + u], fj);
 #pragma unroll
           for (int u = 0; u < U; ++u)
-            cstep_resolve<BIL>(sa[u], tz[i + u], cam_h, horizon, kw + ((uint32_t)u << FSB_ROW_BITS), st);
-          /* next set: the following steps of this block, or the head of the next block (a repeated last sample in the
+            cstep_resolve<BIL>(sa[u], tz[i + u], cam_h, horizon, kw + ((uint32_t)(i + u) << FSB_ROW_BITS), st);
+          /* next set: the following steps of this chunk, or the head of the next one (a repeated last sample in the
            * padding projects to the same row and `occlude` keeps the earlier one) */
-          const float4 *nx = i + 2 * U < 32 ? tl + i + 2 * U : tl_next;
 #pragma unroll
-          for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, nx[u], fj);
+          for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, i + 2 * U < 32 ? tl[i + 2 * U + u] : tl_next[u], fj);
 #pragma unroll
           for (int u = 0; u < U; ++u)
-            cstep_resolve<BIL>(sb[u], tz[i + U + u], cam_h, horizon, kw + ((uint32_t)(U + u) << FSB_ROW_BITS), st);
+            cstep_resolve<BIL>(sb[u], tz[i + U + u], cam_h, horizon, kw + ((uint32_t)(i + U + u) << FSB_ROW_BITS), st);
         }
       }
       cp_async_wait_all();
-      if (!__syncthreads_or(active)) break; /* block c + 2 visible; everyone is done with block c */
+      if (!__syncthreads_or(active)) break; /* chunk c + 2 visible; everyone is done with chunk c */
       slot = slot1;
     }
   }
-  if (jrel - lane < ncols) a.cand_cnt[lid] = (uint32_t)st.n;
-  if (a.stats && jrel - lane < ncols) {
-    /* in chunks of 32 samples of one column, like the lanes-over-depth march counts them */
-    if (lane == 0) atomicAdd(a.stats, (unsigned long long)c_done * (unsigned long long)min(32, ncols - (jrel - lane)));
-    const unsigned long long n = (jrel < ncols) ? (unsigned long long)st.n : 0ull;
-    unsigned long long tot = n;
+  if (group * 32 < ncols) {
+    a.cand_cnt[((size_t)pose * a.n_seg + seg) * a.ncols_pad + jrel] = (uint32_t)st.n;
+    if (a.stats) {
+      /* in chunks of 32 samples of one column, like the lanes-over-depth march counts them */
+      if (lane == 0) atomicAdd(a.stats, (unsigned long long)c_done * (unsigned long long)min(32, ncols - group * 32));
+      unsigned long long tot = (jrel < ncols) ? (unsigned long long)st.n : 0ull;
 #pragma unroll
-    for (int d = 16; d; d >>= 1) tot += __shfl_xor_sync(FSB_FULL, tot, d);
-    if (lane == 0) atomicAdd(a.stats + 1, tot);
+      for (int d = 16; d; d >>= 1) tot += __shfl_xor_sync(FSB_FULL, tot, d);
+      if (lane == 0) atomicAdd(a.stats + 1, tot);
+    }
   }
 }
 
@@ -229,11 +246,11 @@ __global__ void __launch_bounds__(128) fsb_merge_kernel(const fsb_render_args a)
   const int ncols = a.col_end - a.col_begin;
   const int col = blockIdx.x * 4 + warp;
   if (col >= ncols) return;
-  const int S = a.n_seg;
-  const size_t lid = ((size_t)pose * S + min(lane, S - 1)) * a.ncols_pad + col;
-  const uint32_t *list = a.cand + lid * a.cand_cap;
+  const int S = a.n_seg, s = min(lane, S - 1);
+  const size_t lid = ((size_t)pose * S + s) * a.ncols_pad + col;
+  const uint32_t *list = a.cand + cand_group_base(a, pose, s, col >> 5) + (col & 31); /* entry p at list[p * 32] */
   const int n = lane < S ? (int)a.cand_cnt[lid] : 0;
-  const int fin = n ? (int)(list[n - 1] & FSB_ROW_MASK) : a.h;
+  const int fin = n ? (int)(list[(size_t)(n - 1) * 32] & FSB_ROW_MASK) : a.h;
   int incl = fin;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -246,7 +263,7 @@ __global__ void __launch_bounds__(128) fsb_merge_kernel(const fsb_render_args a)
   while (__any_sync(FSB_FULL, lo < hi)) {
     if (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if ((int)(list[mid] & FSB_ROW_MASK) >= carry) lo = mid + 1;
+      if ((int)(list[(size_t)mid * 32] & FSB_ROW_MASK) >= carry) lo = mid + 1;
       else hi = mid;
     }
   }
@@ -262,14 +279,15 @@ __global__ void __launch_bounds__(128) fsb_merge_kernel(const fsb_render_args a)
   /* bands at or above the last visible record: every record of the list has a row >= theirs */
   const int last_row = __shfl_sync(FSB_FULL, incl, 31);
   const int last_band = total ? (last_row >> a.rb_shift) : a.n_bands;
-  uint32_t *sidx = a.sidx + ((size_t)pose * ncols + col) * (a.n_bands + 1);
-  for (int b = lane; b <= last_band; b += 32) sidx[b] = (uint32_t)total;
+  uint32_t *sidx = a.sidx + ((size_t)pose * (a.ncols_pad >> 5) + (col >> 5)) * (a.n_bands + 1) * 32 + (col & 31);
+  for (int b = lane; b <= last_band; b += 32) sidx[b * 32] = (uint32_t)total;
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* Colour: one warp per (pose, column[, segment]), lane = record.  Reads the sample index, rebuilds the sample position
- * (get_segment, :63-66), runs png_color / png_color_filtered and writes the record the expand kernels consume, plus the
- * per-band index of the list (sidx[b] = number of records with row >= b * 32; rows strictly decrease along the list).
+/* Colour: one warp per (pose, group of 32 columns[, segment]), lane = column, one record per lane and trip.  Reads the
+ * sample index, rebuilds the sample position (get_segment, :63-66), runs png_color / png_color_filtered and writes the
+ * record the expand kernels consume, plus the per-band index of the list (sidx[b] = number of records with
+ * row >= b * 32; rows strictly decrease along the list).
  *
  * The bilinear filter is the unit-weight, alpha 0x00/0xFF form of fsb_device.cuh (sample_color) spelled for this pass:
  *   - ceil x = floor x + (x > floor x), as in the march: two FRND instead of four;
@@ -291,7 +309,8 @@ __device__ __forceinline__ uint32_t colour_channel(float v00, float v01, float v
 }
 
 template <bool BIL>
-__device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x, float y, const float *un, const float *sq) {
+__device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x, float y, const float *un, const float *sq,
+                                              const float *sq_sm) {
   if (!BIL) return sample_color<MEM_TEX, false, FSB_F2I_SATURATE>(a, x, y, un, sq);
   const float fx = floorf(x), fy = floorf(y);
   const float wx1 = __fsub_rn(x, fx), wy1 = __fsub_rn(y, fy);
@@ -303,9 +322,9 @@ __device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x,
     FSB_TLD4_F32C("b", a.tex_f, u, v, r10, r11, r01, r00); /* channel order of the RGBA8 texel is {B, G, R, height} */
     FSB_TLD4_F32C("g", a.tex_f, u, v, g10, g11, g01, g00);
     FSB_TLD4_F32C("r", a.tex_f, u, v, b10, b11, b01, b00);
-    const uint32_t r = colour_channel(r00, r01, r10, r11, wx0, wx1, wy0, wy1, sq);
-    const uint32_t g = colour_channel(g00, g01, g10, g11, wx0, wx1, wy0, wy1, sq);
-    const uint32_t b = colour_channel(b00, b01, b10, b11, wx0, wx1, wy0, wy1, sq);
+    const uint32_t r = colour_channel(r00, r01, r10, r11, wx0, wx1, wy0, wy1, sq_sm);
+    const uint32_t g = colour_channel(g00, g01, g10, g11, wx0, wx1, wy0, wy1, sq_sm);
+    const uint32_t b = colour_channel(b00, b01, b10, b11, wx0, wx1, wy0, wy1, sq_sm);
     /* low bytes of b, g, r under the alpha byte */
     return (__byte_perm(__byte_perm(b, g, 0x0040), r, 0x7410) & 0x00FFFFFFu) | al;
   }
@@ -314,75 +333,79 @@ __device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x,
 
 template <bool BIL>
 __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a) {
+  __shared__ float sq_sm[256]; /* (c/255)^2: the second-stage operands of the three mixes */
   const float *un = a.lut, *sq = a.lut + 256;
+  sq_sm[threadIdx.x] = sq[threadIdx.x];
+  sq_sm[threadIdx.x + 128] = sq[threadIdx.x + 128];
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pose = blockIdx.z, seg = blockIdx.y;
   const int ncols = a.col_end - a.col_begin;
-  const int col = blockIdx.x * 4 + warp;
-  if (col >= ncols) return;
-  const size_t lid = ((size_t)pose * a.n_seg + seg) * a.ncols_pad + col;
-  const uint32_t *src = a.cand + lid * a.cand_cap;
-  int n, off = 0, prev_band = a.n_bands;
+  const int group = blockIdx.x * 4 + warp;
+  if (group * 32 >= ncols) return;
+  const int jrel = group * 32 + lane;
+  const size_t lid = ((size_t)pose * a.n_seg + seg) * a.ncols_pad + jrel;
+  const uint32_t *src = a.cand + cand_group_base(a, pose, seg, group) + lane; /* entry p at src[p * 32] */
+  int n, off = 0, pb = a.n_bands;
   if (a.n_seg > 1) {
     const uint4 info = a.seg_info[lid];
-    src += info.x;
+    src += (size_t)info.x * 32;
     off = (int)info.y;
-    if ((int)info.z < a.h) prev_band = (int)(info.z >> a.rb_shift);
+    if ((int)info.z < a.h) pb = (int)(info.z >> a.rb_shift);
     n = (int)info.w;
   } else {
     n = (int)a.cand_cnt[lid];
   }
-  const size_t colid = (size_t)pose * ncols + col;
-  uint32_t *sidx = a.sidx + colid * (a.n_bands + 1);
-  uint32_t *rec4 = reinterpret_cast<uint32_t *>(a.recs) + colid * a.rec_cap + 1 + off;
-  uint2 *rec8 = a.recs + colid * a.rec_cap + 1 + off;
-  if (seg == 0 && lane == 0) { /* slot 0: the guard record the 8-byte walks stop at (see fsb_kernels.cu) */
-    if (a.rec4) rec4[-1] = 0u;
-    else rec8[-1] = make_uint2(0xffffffffu, 0u);
+  if (jrel >= ncols) n = 0; /* padding lanes of a ragged group */
+  const size_t gid = (size_t)pose * (a.ncols_pad >> 5) + group;
+  uint32_t *sidx = a.sidx + gid * (a.n_bands + 1) * 32 + lane;                 /* sidx[b] at sidx[b * 32]         */
+  const size_t rec0 = (gid * a.rec_cap + 1 + off) * 32 + lane;                  /* record off + p at rec[p * 32]   */
+  uint32_t *rec4 = reinterpret_cast<uint32_t *>(a.recs) + rec0;
+  uint2 *rec8 = a.recs + rec0;
+  if (seg == 0) { /* slot 0: the guard record the 8-byte walks stop at (see fsb_kernels.cu) */
+    if (a.rec4) reinterpret_cast<uint32_t *>(a.recs)[gid * a.rec_cap * 32 + lane] = 0u;
+    else a.recs[gid * a.rec_cap * 32 + lane] = make_uint2(0xffffffffu, 0u);
   }
-  const float *tab = a.table + (size_t)pose * a.tab_stride;
-  const float fj = (float)(a.col_begin + col);
-  /* the candidate word and the depth-table entry of the next 32 records are fetched while this chunk is filtered */
+  const float4 *line = reinterpret_cast<const float4 *>(a.table + (size_t)pose * a.tab_stride);
+  const float fj = (float)(a.col_begin + jrel);
+  /* the candidate word and the depth-table entry of the next trip are fetched while this one is filtered */
   uint32_t word_n = 0;
   float4 l_n = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane < n) {
-    word_n = src[lane];
-    const uint32_t k = word_n >> FSB_ROW_BITS;
-    l_n = __ldg(reinterpret_cast<const float4 *>(tab + (k >> 5) * FSB_TAB_BLOCK) + (k & 31));
+  if (0 < n) {
+    word_n = src[0];
+    l_n = __ldg(line + (word_n >> FSB_ROW_BITS));
   }
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
-    const bool valid = i < n;
+  for (int p = 0; __any_sync(FSB_FULL, p < n); ++p) {
+    const bool valid = p < n;
     const uint32_t word = word_n;
     const float4 l = l_n;
-    if (i + 32 < n) {
-      word_n = src[i + 32];
-      const uint32_t k = word_n >> FSB_ROW_BITS;
-      l_n = __ldg(reinterpret_cast<const float4 *>(tab + (k >> 5) * FSB_TAB_BLOCK) + (k & 31));
+    if (p + 1 < n) {
+      word_n = src[(size_t)(p + 1) * 32];
+      l_n = __ldg(line + (word_n >> FSB_ROW_BITS));
     }
-    const uint32_t row = word & FSB_ROW_MASK;
     if (valid) {
+      const uint32_t row = word & FSB_ROW_MASK;
       const float x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
       const float y = __fadd_rn(l.y, __fmul_rn(fj, l.w));
-      const uint32_t colour = colour_of<BIL>(a, x, y, un, sq);
-      if (a.rec4) rec4[i] = (colour & 0x80FFFFFFu) | ((row & 31u) << 24);
-      else rec8[i] = make_uint2(a.smooth ? word : row, colour);
-    }
-    /* band index: the record that opens a new band writes the list position for every band it skipped */
-    const int band = (int)(row >> a.rb_shift);
-    int pb = __shfl_up_sync(FSB_FULL, band, 1);
-    if (lane == 0) pb = prev_band;
-    if (valid && band < pb) {
-      int b = pb;
+      const uint32_t colour = colour_of<BIL>(a, x, y, un, sq, sq_sm);
+      if (a.rec4) rec4[(size_t)p * 32] = (colour & 0x80FFFFFFu) | ((row & 31u) << 24);
+      else rec8[(size_t)p * 32] = make_uint2(a.smooth ? word : row, colour);
+      /* band index: the record that opens a new band writes its list position for every band it skipped */
+      const int band = (int)(row >> a.rb_shift);
+      if (band < pb) {
+        int b = pb;
 #pragma unroll 1
-      do sidx[b] = (uint32_t)(off + i);
-      while (--b > band);
+        do sidx[b * 32] = (uint32_t)(off + p);
+        while (--b > band);
+        pb = band;
+      }
     }
-    prev_band = __shfl_sync(FSB_FULL, band, min(n - base, 32) - 1);
   }
-  /* unsplit series: bands at or above the last record */
-  if (a.n_seg == 1)
-    for (int b = lane; b <= prev_band; b += 32) sidx[b] = (uint32_t)n;
+  /* unsplit series: bands at or above the last record (fsb_merge_kernel writes them for a split one) */
+  if (a.n_seg == 1 && jrel < ncols) {
+#pragma unroll 1
+    for (int b = pb; b >= 0; --b) sidx[b * 32] = (uint32_t)n;
+  }
 }
 
 /* ------------------------------------------------------------------------------------------ */
