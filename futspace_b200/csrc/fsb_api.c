@@ -33,9 +33,8 @@ typedef struct fsb_scratch {
   void *recs;                     /* march -> expand record lists */
   uint32_t *sidx;
   size_t recs_cap, sidx_cap;      /* bytes */
-  uint32_t *cand, *cand_cnt;      /* column-parallel march: candidate lists, their lengths, merge results */
-  uint4_fsb *seg_info;
-  size_t cand_cap, cand_cnt_cap, seg_info_cap; /* bytes */
+  uint32_t *cand, *cand_cnt;      /* column-parallel march: candidate lists and their lengths */
+  size_t cand_cap, cand_cnt_cap;  /* bytes */
 } fsb_scratch;
 
 struct fsb_context {
@@ -241,7 +240,6 @@ void fsb_context_free(fsb_context *ctx) {
     cudaFree(sc->sidx);
     cudaFree(sc->cand);
     cudaFree(sc->cand_cnt);
-    cudaFree(sc->seg_info);
     cudaEventDestroy(sc->fc_free);
     cudaEventDestroy(sc->coloured);
     cudaEventDestroy(sc->expanded);
@@ -480,7 +478,6 @@ static int ensure_tables(fsb_context *ctx, fsb_scratch *sc, int n_poses, int tab
 #define FSB_MAX_H 32768
 #define FSB_SCRATCH_BUDGET ((size_t)8192 << 20)
 #define FSB_COLS_MAX_NZ (1 << 17)        /* candidate word of the column-parallel march: row (15 bits) | sample index (17 bits) */
-#define FSB_MAX_SEG 32                   /* depth segments per column (fsb_merge_kernel: lane = segment) */
 
 static int grow(fsb_context *ctx, void **ptr, size_t *cap, size_t need) {
   if (need <= *cap) return FSB_OK;
@@ -499,8 +496,8 @@ typedef struct {
   int mem;        /* FSB_MEM_* */
   int cols;       /* column-parallel march (fsb_march_cols.cu) */
   int rec4;       /* 4-byte records */
-  int n_seg;      /* warps per column's depth series */
-  int cand_cap;   /* candidate words per (column, segment) */
+  int cand_cap;   /* candidate words per column */
+  int slice_len;  /* colour pass: records per warp (0: whole lists) */
   int ncols_pad;
 } render_plan;
 
@@ -512,10 +509,9 @@ static int ensure_scratch(fsb_context *ctx, fsb_scratch *sc, int n_poses, int nc
   if ((rc = grow(ctx, &sc->recs, &sc->recs_cap, np * lc * (h + 1) * (pl->rec4 ? 4 : 8)))) return rc;
   if ((rc = grow(ctx, (void **)&sc->sidx, &sc->sidx_cap, np * lc * (n_bands + 1) * 4))) return rc;
   if (pl->cols) {
-    const size_t lists = np * pl->n_seg * pl->ncols_pad;
+    const size_t lists = np * pl->ncols_pad;
     if ((rc = grow(ctx, (void **)&sc->cand, &sc->cand_cap, lists * pl->cand_cap * 4))) return rc;
     if ((rc = grow(ctx, (void **)&sc->cand_cnt, &sc->cand_cnt_cap, lists * 4))) return rc;
-    if (pl->n_seg > 1 && (rc = grow(ctx, (void **)&sc->seg_info, &sc->seg_info_cap, lists * 16))) return rc;
   }
   return FSB_OK;
 }
@@ -640,7 +636,6 @@ static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_cam
   render_plan pl;
   memset(&pl, 0, sizeof pl);
   pl.mem = FSB_MEM_PLANES;
-  pl.n_seg = 1;
   const int ncols = col_end - col_begin;
   const int smooth = (prm->flags & FSB_FLAG_SMOOTHING) ? 1 : 0;
   /* The texture path addresses texels with normalised coordinates (floor(x) + 1) / size and relies on that point
@@ -665,22 +660,21 @@ static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_cam
    * round 1 keeps the tiled / generic paths, very long series, and FSB_FLAG_MARCH_Z (A/B). */
   pl.cols = pl.mem == FSB_MEM_TEX && max_nz <= FSB_COLS_MAX_NZ && !(prm->flags & FSB_FLAG_MARCH_Z) && !ctx->force_march_z;
   pl.ncols_pad = (ncols + 31) & ~31;
-  const int n_chunks = (max_nz + 31) / 32;
   if (pl.cols) {
-    /* enough warps to fill the device: one per 32 columns and depth segment; batches need no split */
-    const long long groups = (long long)(pl.ncols_pad / 32) * n;
-    const long long want = (long long)ctx->sm_count * 12;
-    long long seg = groups >= want ? 1 : (want + groups - 1) / groups;
-    if (seg > FSB_MAX_SEG) seg = FSB_MAX_SEG;
-    if (seg > n_chunks) seg = n_chunks;
-    if (seg < 1) seg = 1;
-    const char *env = getenv("FSB_SEGMENTS"); /* tuning aid: depth segments per column */
-    if (env && atoi(env) > 0) seg = atoi(env) > FSB_MAX_SEG ? FSB_MAX_SEG : atoi(env);
-    if (seg > n_chunks && n_chunks > 0) seg = n_chunks;
-    pl.n_seg = (int)seg;
-    const int seg_steps = 32 * ((n_chunks + pl.n_seg - 1) / pl.n_seg);
-    pl.cand_cap = seg_steps < h ? seg_steps : h;
+    /* one march warp per 32 columns: a launch group must offer enough of them to fill the device */
+    const long long warps = (long long)(pl.ncols_pad / 32) * n;
+    long long min_warps = (long long)ctx->sm_count * 4;
+    const char *env = getenv("FSB_COLS_MIN_WARPS"); /* tuning aid */
+    if (env && atoi(env) >= 0) min_warps = atoi(env);
+    if (warps < min_warps) pl.cols = 0;
+  }
+  if (pl.cols) {
+    pl.cand_cap = max_nz < h ? max_nz : h; /* one candidate per depth sample at most, and rows strictly decrease */
     if (pl.cand_cap < 1) pl.cand_cap = 1;
+    /* colour pass: whole lists per warp when there are plenty of them, otherwise slices of 32 records */
+    pl.slice_len = (long long)(pl.ncols_pad / 32) * n >= (long long)ctx->sm_count * 160 ? 0 : 32;
+    const char *env = getenv("FSB_COLOUR_SLICE");
+    if (env && atoi(env) >= 0) pl.slice_len = atoi(env);
   }
   if ((rc = ensure_scratch(ctx, sc, n, ncols, h, &pl))) return rc;
   if (sc->busy) { /* an earlier group's expand still reads this scratch set (and its pose constants) */
@@ -742,15 +736,12 @@ static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_cam
   a.lut = ctx->lut;
   a.cand = sc->cand;
   a.cand_cnt = sc->cand_cnt;
-  a.seg_info = sc->seg_info;
-  a.n_seg = pl.n_seg;
   a.cand_cap = pl.cand_cap;
   a.ncols_pad = pl.ncols_pad;
   if (pl.cols) {
-    /* few warps per SM (split series): deeper gather pipeline per warp */
-    CU(ctx, (cudaError_t)fsb_launch_march_cols(&a, pl.n_seg > 1, ctx->stream, &ctx->launches));
+    CU(ctx, (cudaError_t)fsb_launch_march_cols(&a, ctx->stream, &ctx->launches));
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
-    CU(ctx, (cudaError_t)fsb_launch_colour(&a, ctx->stream, &ctx->launches));
+    CU(ctx, (cudaError_t)fsb_launch_colour(&a, pl.slice_len, ctx->stream, &ctx->launches));
   } else {
     CU(ctx, (cudaError_t)fsb_launch_march(&a, pl.mem, ctx->stream, &ctx->launches));
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));

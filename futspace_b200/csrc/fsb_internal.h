@@ -28,11 +28,6 @@ typedef uint2 uint2_fsb;
 #else
 typedef struct { uint32_t x, y; } uint2_fsb;
 #endif
-#ifdef __CUDACC__
-typedef uint4 uint4_fsb;
-#else
-typedef struct { uint32_t x, y, z, w; } uint4_fsb;
-#endif
 
 typedef struct fsb_render_args {
   const uint32_t *packed;   /* height<<24 | rgb in 8x4-texel tiles (fsb_kernels.cu texel_x/texel_y), or NULL */
@@ -64,13 +59,11 @@ typedef struct fsb_render_args {
   int32_t rec4;             /* 1: 4-byte records (row & 31) << 24 | alpha flag << 31 | rgb (packed maps, alpha 0x00 / 0xFF) */
   int32_t smooth;           /* smoothing #on: record .x = row | sample index << 15 (fsb_expand_smooth_kernel) */
   unsigned long long *stats; /* optional (profiling): [0] += chunks of 32 samples evaluated, [1] += records emitted */
-  /* column-parallel march (fsb_march_cols.cu): per (pose, depth segment, column) a candidate list of
-   * row | sample index << 15 words, its length, and -- when the series is split -- what fsb_merge_kernel derived */
-  uint32_t *cand;           /* [n_poses][n_seg][ncols_pad][cand_cap]                                          */
-  uint32_t *cand_cnt;       /* [n_poses][n_seg][ncols_pad]                                                    */
-  uint4_fsb *seg_info;      /* [n_poses][n_seg][ncols_pad] {first visible candidate, offset in the column's list, carried row, visible count} */
-  int32_t n_seg;            /* warps a column's depth series is split over (1: batches)                       */
-  int32_t cand_cap;         /* >= min(h, depth samples per segment)                                           */
+  /* column-parallel march (fsb_march_cols.cu): per (pose, group of 32 columns) the interleaved candidate lists of
+   * row | sample index << 15 words, and per column the list length */
+  uint32_t *cand;           /* [n_poses][ncols_pad / 32][cand_cap][32]                                        */
+  uint32_t *cand_cnt;       /* [n_poses][ncols_pad]                                                           */
+  int32_t cand_cap;         /* >= min(h, depth samples)                                                       */
   int32_t ncols_pad;        /* columns rounded up to a multiple of 32                                         */
   int32_t full_eval;        /* FSB_FLAG_NO_CULL: also no early exit when the y-buffer reaches row 0           */
   const float *lut;         /* c/255 [0..255] and its square [256..511] (device, filled once per device)      */
@@ -87,10 +80,10 @@ int fsb_launch_setup(const fsb_frame_consts *fc_dev, const fsb_frame_consts *sin
 #define FSB_MEM_TEX 2
 int fsb_launch_march(const fsb_render_args *a, int mem, void *stream, int64_t *launches);
 int fsb_launch_expand(const fsb_render_args *a, void *stream, int64_t *launches);
-/* column-parallel march of the texture path (fsb_march_cols.cu); deep != 0: more gathers in flight per warp */
-int fsb_launch_march_cols(const fsb_render_args *a, int deep, void *stream, int64_t *launches);
-/* merge (n_seg > 1) + colour pass: candidate lists -> the records fsb_launch_expand consumes */
-int fsb_launch_colour(const fsb_render_args *a, void *stream, int64_t *launches);
+/* column-parallel march of the texture path (fsb_march_cols.cu) */
+int fsb_launch_march_cols(const fsb_render_args *a, void *stream, int64_t *launches);
+/* colour pass: candidate lists -> the records fsb_launch_expand consumes; slice_len: records per warp (0: whole lists) */
+int fsb_launch_colour(const fsb_render_args *a, int slice_len, void *stream, int64_t *launches);
 const float *fsb_lut_device_address(void); /* after fsb_launch_lut_init */
 int fsb_launch_lut_init(void *stream); /* fills the colour look-up table of the march (once per device, before any render) */
 int fsb_launch_shadow(const uint32_t *color, const int32_t *height, int q, int r, const float *sun, int out_q, int out_r,

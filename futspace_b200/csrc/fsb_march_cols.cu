@@ -3,8 +3,6 @@
  *
  *   fsb_marchc_kernel   lane = screen column, the warp walks the depth series; per-lane y-buffer in a register;
  *                       emits, per column, the candidate list (row | sample index << 15)          fut/voxel_renderer.fut:215-231
- *   fsb_merge_kernel    (depth range split over several warps only) which candidates of a segment survive the
- *                       y-buffer carried in from the nearer segments, and where they land in the column's list  :231
  *   fsb_colour_kernel   one thread per visible record: png_color / png_color_filtered (3 x argb.mix) and the band index
  *                       of the list -> the (row, colour) records fsb_expand*_kernel consumes      fut/render_functions.fut:91-105
  *
@@ -18,10 +16,10 @@
  *   - The colour filter (33 divides + 9 square roots per sample in the reference) only runs for samples that are
  *     visible, on full warps, in its own pass: the march keeps no colour state, which is what lets it run at 40+
  *     warps per SM.
- *   - A column's depth range can be split over S warps (single frames: 60 column groups cannot fill 148 SMs).  Each
- *     segment marches against its own y-buffer; a candidate of segment s is visible iff its row is below the minimum
- *     of all nearer segments (`occlude` is associative, :69-72) -- rows decrease along a list, so the survivors are a
- *     suffix, found by one binary search per (column, segment) in fsb_merge_kernel.
+ *   - Batches only: a frame offers one warp per 32 columns (60 at 1920), so single frames and small batches stay on the
+ *     lanes-over-depth march (one warp per column).  Splitting a column's depth series over several warps with a merge
+ *     pass was built and measured in round 2: the candidates of the far segments, the merge and the extra
+ *     launches cost more than the split saved.
  *
  * Float discipline as in fsb_kernels.cu: every parity-relevant operation uses the round-to-nearest intrinsics.
  */
@@ -110,14 +108,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 /* Scratch layout of this file (and of the expand kernels behind it, list_view in fsb_kernels.cu): the lists of the 32
  * columns of a group are interleaved -- entry p of lane l at (p * 32 + l) words from the group's base -- because every
  * kernel here has lane = column: appends of neighbouring columns share 128-byte lines instead of touching 32. */
-__device__ __forceinline__ size_t cand_group_base(const fsb_render_args &a, int pose, int seg, int group) {
-  return (((size_t)pose * a.n_seg + seg) * (a.ncols_pad >> 5) + group) * a.cand_cap * 32;
+__device__ __forceinline__ size_t cand_group_base(const fsb_render_args &a, int pose, int group) {
+  return ((size_t)pose * (a.ncols_pad >> 5) + group) * a.cand_cap * 32;
 }
 
 /* U = depth steps per register set; two sets are in flight (the gathers of one are issued before the other is resolved).
  *
  * Depth table: the 640 bytes of a chunk of 32 steps ({sx,sy,dx,dy} x 32, inv_z x 32) are the same for every column, so
- * the CTA (4 warps = 128 adjacent columns of one pose and depth segment) stages them in shared memory with cp.async, two
+ * the CTA (4 warps = 128 adjacent columns of one pose) stages them in shared memory with cp.async, two
  * chunks ahead of the one being marched: the per-step operands are LDS broadcasts (29 cycles) instead of global loads
  * queued behind the texture gathers in the same L1 pipe (round-2 ncu: the largest stall site of the first version). */
 template <bool BIL, int U, int MINB>
@@ -125,7 +123,7 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
   static_assert(32 % (2 * U) == 0, "a pair of register sets must tile a 32-step chunk");
   __shared__ __align__(16) float sm[3][FSB_TAB_BLOCK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pose = blockIdx.z, seg = blockIdx.y;
+  const int pose = blockIdx.y;
   const int ncols = a.col_end - a.col_begin;
   const int group = blockIdx.x * FSB_MC_WARPS + warp;
   const int jrel = group * 32 + lane;
@@ -141,13 +139,12 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
   const float *invz = a.table + (size_t)pose * a.tab_stride + 4 * (size_t)kcap;                 /* inv_z[k] (:217)  */
   col_state st;
   st.ybuf_f = (float)a.h;
-  st.list = a.cand + (active ? cand_group_base(a, pose, seg, group) : 0) + lane;
+  st.list = a.cand + (active ? cand_group_base(a, pose, group) : 0) + lane;
   st.n = 0;
   const float fj = (float)(a.col_begin + jrel);
 
-  /* this CTA's share of the depth series, in chunks of 32 samples */
-  int c_first = (int)(((long long)n_chunks * seg) / a.n_seg);
-  const int c_end = (int)(((long long)n_chunks * (seg + 1)) / a.n_seg);
+  int c_first = 0;
+  const int c_end = n_chunks; /* the depth series in chunks of 32 samples */
   /* Occlusion bound (see fsb_kernels.cu): camera above the highest terrain -> a prefix of the series projects below the
    * bottom row and is skipped (lane = chunk, bound at the chunk's last sample) ... */
   if (cull_d >= 0.0f && cull_d < INFINITY) {
@@ -225,7 +222,7 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
     }
   }
   if (group * 32 < ncols) {
-    a.cand_cnt[((size_t)pose * a.n_seg + seg) * a.ncols_pad + jrel] = (uint32_t)st.n;
+    a.cand_cnt[(size_t)pose * a.ncols_pad + jrel] = (uint32_t)st.n;
     if (a.stats) {
       /* in chunks of 32 samples of one column, like the lanes-over-depth march counts them */
       if (lane == 0) atomicAdd(a.stats, (unsigned long long)c_done * (unsigned long long)min(32, ncols - group * 32));
@@ -235,52 +232,6 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
       if (lane == 0) atomicAdd(a.stats + 1, tot);
     }
   }
-}
-
-/* ------------------------------------------------------------------------------------------ */
-/* Merge (n_seg > 1): one warp per (pose, column), lane = segment.  The carry into segment s is the minimum row of all
- * nearer segments (or h); its candidates with row < carry are visible -- a suffix, rows decrease along a list. */
-__global__ void __launch_bounds__(128) fsb_merge_kernel(const fsb_render_args a) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pose = blockIdx.y;
-  const int ncols = a.col_end - a.col_begin;
-  const int col = blockIdx.x * 4 + warp;
-  if (col >= ncols) return;
-  const int S = a.n_seg, s = min(lane, S - 1);
-  const size_t lid = ((size_t)pose * S + s) * a.ncols_pad + col;
-  const uint32_t *list = a.cand + cand_group_base(a, pose, s, col >> 5) + (col & 31); /* entry p at list[p * 32] */
-  const int n = lane < S ? (int)a.cand_cnt[lid] : 0;
-  const int fin = n ? (int)(list[(size_t)(n - 1) * 32] & FSB_ROW_MASK) : a.h;
-  int incl = fin;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int o = __shfl_up_sync(FSB_FULL, incl, d);
-    if (lane >= d) incl = min(incl, o);
-  }
-  int carry = __shfl_up_sync(FSB_FULL, incl, 1);
-  if (lane == 0) carry = a.h;
-  int lo = 0, hi = n; /* first index with row < carry */
-  while (__any_sync(FSB_FULL, lo < hi)) {
-    if (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((int)(list[(size_t)mid * 32] & FSB_ROW_MASK) >= carry) lo = mid + 1;
-      else hi = mid;
-    }
-  }
-  const int vis = n - lo;
-  int off = vis;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int o = __shfl_up_sync(FSB_FULL, off, d);
-    if (lane >= d) off += o;
-  }
-  const int total = __shfl_sync(FSB_FULL, off, 31);
-  if (lane < S) a.seg_info[lid] = make_uint4((uint32_t)lo, (uint32_t)(off - vis), (uint32_t)carry, (uint32_t)vis);
-  /* bands at or above the last visible record: every record of the list has a row >= theirs */
-  const int last_row = __shfl_sync(FSB_FULL, incl, 31);
-  const int last_band = total ? (last_row >> a.rb_shift) : a.n_bands;
-  uint32_t *sidx = a.sidx + ((size_t)pose * (a.ncols_pad >> 5) + (col >> 5)) * (a.n_bands + 1) * 32 + (col & 31);
-  for (int b = lane; b <= last_band; b += 32) sidx[b * 32] = (uint32_t)total;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -331,58 +282,59 @@ __device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x,
   return sample_color<MEM_TEX, true, FSB_F2I_SATURATE>(a, x, y, un, sq);
 }
 
+/* slice_len > 0: blockIdx.y selects a slice of the record index range (medium batches: more, shorter warps); the last
+ * slice runs to the end of the list.  slice_len == 0: the whole list. */
 template <bool BIL>
-__global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a) {
+__global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a, int slice_len) {
   __shared__ float sq_sm[256]; /* (c/255)^2: the second-stage operands of the three mixes */
   const float *un = a.lut, *sq = a.lut + 256;
   sq_sm[threadIdx.x] = sq[threadIdx.x];
   sq_sm[threadIdx.x + 128] = sq[threadIdx.x + 128];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pose = blockIdx.z, seg = blockIdx.y;
+  const int pose = blockIdx.z;
   const int ncols = a.col_end - a.col_begin;
   const int group = blockIdx.x * 4 + warp;
   if (group * 32 >= ncols) return;
   const int jrel = group * 32 + lane;
-  const size_t lid = ((size_t)pose * a.n_seg + seg) * a.ncols_pad + jrel;
-  const uint32_t *src = a.cand + cand_group_base(a, pose, seg, group) + lane; /* entry p at src[p * 32] */
-  int n, off = 0, pb = a.n_bands;
-  if (a.n_seg > 1) {
-    const uint4 info = a.seg_info[lid];
-    src += (size_t)info.x * 32;
-    off = (int)info.y;
-    if ((int)info.z < a.h) pb = (int)(info.z >> a.rb_shift);
-    n = (int)info.w;
-  } else {
-    n = (int)a.cand_cnt[lid];
+  int n = jrel < ncols ? (int)a.cand_cnt[(size_t)pose * a.ncols_pad + jrel] : 0; /* padding lanes of a ragged group: none */
+  int p = 0, p_end = n;
+  bool closes = jrel < ncols; /* this warp handles the column's last record (or its empty list): it closes the band index */
+  if (slice_len > 0) {
+    p = (int)blockIdx.y * slice_len;
+    if (blockIdx.y + 1 < gridDim.y) p_end = min(n, p + slice_len);
+    closes = closes && (int)blockIdx.y == (n == 0 ? 0 : min((n - 1) / slice_len, (int)gridDim.y - 1));
   }
-  if (jrel >= ncols) n = 0; /* padding lanes of a ragged group */
+  if (!__any_sync(FSB_FULL, p < p_end || closes)) return;
+  const uint32_t *src = a.cand + cand_group_base(a, pose, group) + lane; /* entry q at src[q * 32] */
   const size_t gid = (size_t)pose * (a.ncols_pad >> 5) + group;
   uint32_t *sidx = a.sidx + gid * (a.n_bands + 1) * 32 + lane;                 /* sidx[b] at sidx[b * 32]         */
-  const size_t rec0 = (gid * a.rec_cap + 1 + off) * 32 + lane;                  /* record off + p at rec[p * 32]   */
+  const size_t rec0 = (gid * a.rec_cap + 1) * 32 + lane;                        /* record q at rec[q * 32]         */
   uint32_t *rec4 = reinterpret_cast<uint32_t *>(a.recs) + rec0;
   uint2 *rec8 = a.recs + rec0;
-  if (seg == 0) { /* slot 0: the guard record the 8-byte walks stop at (see fsb_kernels.cu) */
-    if (a.rec4) reinterpret_cast<uint32_t *>(a.recs)[gid * a.rec_cap * 32 + lane] = 0u;
-    else a.recs[gid * a.rec_cap * 32 + lane] = make_uint2(0xffffffffu, 0u);
+  if (blockIdx.y == 0) { /* slot 0: the guard record the 8-byte walks stop at (see fsb_kernels.cu) */
+    if (a.rec4) rec4[-32] = 0u;
+    else rec8[-32] = make_uint2(0xffffffffu, 0u);
   }
   const float4 *line = reinterpret_cast<const float4 *>(a.table + (size_t)pose * a.tab_stride);
   const float fj = (float)(a.col_begin + jrel);
-  /* the candidate word and the depth-table entry of the next trip are fetched while this one is filtered */
-  uint32_t word_n = 0;
-  float4 l_n = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (0 < n) {
-    word_n = src[0];
-    l_n = __ldg(line + (word_n >> FSB_ROW_BITS));
-  }
-  for (int p = 0; __any_sync(FSB_FULL, p < n); ++p) {
-    const bool valid = p < n;
-    const uint32_t word = word_n;
-    const float4 l = l_n;
-    if (p + 1 < n) {
-      word_n = src[(size_t)(p + 1) * 32];
-      l_n = __ldg(line + (word_n >> FSB_ROW_BITS));
-    }
+  /* band of the record before the slice (n_bands before the first record of the list) */
+  int pb = a.n_bands;
+  if (p > 0 && p < p_end) pb = (int)((src[(size_t)(p - 1) * 32] & FSB_ROW_MASK) >> a.rb_shift);
+  /* Software pipeline: the candidate word two trips ahead and the depth-table entry one trip ahead are in flight while
+   * this trip's record is filtered (the table address depends on the word). */
+  uint32_t word_1 = 0, word_2 = 0;
+  float4 l_1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p < p_end) word_1 = src[(size_t)p * 32];
+  if (p + 1 < p_end) word_2 = src[(size_t)(p + 1) * 32];
+  if (p < p_end) l_1 = __ldg(line + (word_1 >> FSB_ROW_BITS));
+  for (; __any_sync(FSB_FULL, p < p_end); ++p) {
+    const bool valid = p < p_end;
+    const uint32_t word = word_1;
+    const float4 l = l_1;
+    word_1 = word_2;
+    if (p + 2 < p_end) word_2 = src[(size_t)(p + 2) * 32];
+    if (p + 1 < p_end) l_1 = __ldg(line + (word_1 >> FSB_ROW_BITS));
     if (valid) {
       const uint32_t row = word & FSB_ROW_MASK;
       const float x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
@@ -390,19 +342,21 @@ __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a
       const uint32_t colour = colour_of<BIL>(a, x, y, un, sq, sq_sm);
       if (a.rec4) rec4[(size_t)p * 32] = (colour & 0x80FFFFFFu) | ((row & 31u) << 24);
       else rec8[(size_t)p * 32] = make_uint2(a.smooth ? word : row, colour);
-      /* band index: the record that opens a new band writes its list position for every band it skipped */
+      /* band index: the record that opens a new band writes its list position for that band (one predicated store in
+       * the common case) and, rarely, for the bands it skipped */
       const int band = (int)(row >> a.rb_shift);
       if (band < pb) {
-        int b = pb;
+        sidx[(band + 1) * 32] = (uint32_t)p;
+        if (pb - band > 1) {
 #pragma unroll 1
-        do sidx[b * 32] = (uint32_t)(off + p);
-        while (--b > band);
+          for (int b = band + 2; b <= pb; ++b) sidx[b * 32] = (uint32_t)p;
+        }
         pb = band;
       }
     }
   }
-  /* unsplit series: bands at or above the last record (fsb_merge_kernel writes them for a split one) */
-  if (a.n_seg == 1 && jrel < ncols) {
+  /* bands at or above the last record: every record of the list has a row >= theirs */
+  if (closes) {
 #pragma unroll 1
     for (int b = pb; b >= 0; --b) sidx[b * 32] = (uint32_t)n;
   }
@@ -412,12 +366,12 @@ __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a
 template <bool BIL, int U, int MINB>
 static int launch_marchc_t(const fsb_render_args &a, cudaStream_t s) {
   const int ncols = a.col_end - a.col_begin;
-  dim3 grid((ncols + FSB_MC_WARPS * 32 - 1) / (FSB_MC_WARPS * 32), a.n_seg, a.n_poses);
+  dim3 grid((ncols + FSB_MC_WARPS * 32 - 1) / (FSB_MC_WARPS * 32), a.n_poses);
   fsb_marchc_kernel<BIL, U, MINB><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
   return (int)cudaGetLastError();
 }
 
-extern "C" int fsb_launch_march_cols(const fsb_render_args *a, int deep, void *stream, int64_t *launches) {
+extern "C" int fsb_launch_march_cols(const fsb_render_args *a, void *stream, int64_t *launches) {
   cudaStream_t s = (cudaStream_t)stream;
   const bool bil = a->filter == FSB_FILTER_BILINEAR;
   /* tuning aid: FSB_MARCHC_VARIANT = steps per register set / CTAs per SM of the bilinear march */
@@ -430,32 +384,23 @@ extern "C" int fsb_launch_march_cols(const fsb_render_args *a, int deep, void *s
   if (bil && variant == 1) rc = launch_marchc_t<true, 4, 5>(*a, s);
   else if (bil && variant == 2) rc = launch_marchc_t<true, 2, 8>(*a, s);
   else if (bil && variant == 3) rc = launch_marchc_t<true, 2, 10>(*a, s);
-  else if (bil && variant == 4) rc = launch_marchc_t<true, 8, 2>(*a, s);
-  else if (bil && variant == 5) rc = launch_marchc_t<true, 4, 6>(*a, s);
-  else if (bil && variant == 6) rc = launch_marchc_t<true, 4, 4>(*a, s);
-  else if (deep) /* few warps per SM (single frames): more gathers in flight per warp */
-    rc = bil ? launch_marchc_t<true, 8, 2>(*a, s) : launch_marchc_t<false, 8, 2>(*a, s);
+  else if (bil && variant == 4) rc = launch_marchc_t<true, 8, 4>(*a, s);
   else
     rc = bil ? launch_marchc_t<true, 4, 6>(*a, s) : launch_marchc_t<false, 4, 6>(*a, s);
   if (launches) ++*launches;
   return rc;
 }
 
-extern "C" int fsb_launch_colour(const fsb_render_args *a, void *stream, int64_t *launches) {
+/* slice_len: records per colour warp (0: a whole list), see fsb_colour_kernel */
+extern "C" int fsb_launch_colour(const fsb_render_args *a, int slice_len, void *stream, int64_t *launches) {
   cudaStream_t s = (cudaStream_t)stream;
-  const int ncols = a->col_end - a->col_begin;
-  if (a->n_seg > 1) {
-    dim3 mg((ncols + 3) / 4, a->n_poses);
-    fsb_merge_kernel<<<mg, 128, 0, s>>>(*a);
-    if (launches) ++*launches;
-    int rc = (int)cudaGetLastError();
-    if (rc) return rc;
-  }
-  dim3 grid((ncols + 3) / 4, a->n_seg, a->n_poses);
+  const int groups = a->ncols_pad >> 5;
+  const int slices = slice_len > 0 ? (a->cand_cap + slice_len - 1) / slice_len : 1;
+  dim3 grid((groups + 3) / 4, slices, a->n_poses);
   if (a->filter == FSB_FILTER_BILINEAR)
-    fsb_colour_kernel<true><<<grid, 128, 0, s>>>(*a);
+    fsb_colour_kernel<true><<<grid, 128, 0, s>>>(*a, slice_len);
   else
-    fsb_colour_kernel<false><<<grid, 128, 0, s>>>(*a);
+    fsb_colour_kernel<false><<<grid, 128, 0, s>>>(*a, slice_len);
   if (launches) ++*launches;
   return (int)cudaGetLastError();
 }

@@ -48,7 +48,7 @@ def test_tests_variant_golden(fsb, oracle, gpu_ctx, c1w_d1, golden_frames):
     cam = fsb.Camera(512, 800, 78, 0, 100, 800, 1, SKY)
     n0 = gpu_ctx.launch_count
     got = check(fsb, oracle, gpu_ctx, mp, rgb, hgt, cam, fsb.tests_variant_params(), 400, 800)
-    assert gpu_ctx.launch_count - n0 == 5   # set-up, march (depth series split over several warps), merge, colour, expand
+    assert gpu_ctx.launch_count - n0 == 3   # set-up, march, expand
     assert np.array_equal(got, golden_frames["tests_variant_400x800"])
     mp.free()
 
@@ -552,14 +552,18 @@ def test_one_pixel_wide_frame_with_horizon_below_the_frame(fsb, oracle, gpu_ctx,
     mp.free()
 
 
-@pytest.mark.parametrize("segments", [1, 2, 3, 7, 32])
-def test_depth_series_split_over_warps(fsb, oracle, gpu_ctx, fbm1024, monkeypatch, segments):
-    """The column-parallel march may split a column's depth series over several warps (single frames); `occlude`
-    (fut/voxel_renderer.fut:69-72) is associative, so any split must give the frame of the unsplit series -- for both
-    filters, both sentinels, smoothing, ragged widths, a batch with ragged series, and series shorter than the split."""
+@pytest.mark.parametrize("slice_len", [0, 1, 7, 32])
+def test_column_parallel_march_on_single_frames_and_colour_slices(fsb, oracle, gpu_ctx, fbm1024, monkeypatch, slice_len):
+    """The column-parallel march + colour pass is the batch path; FSB_COLS_MIN_WARPS=0 forces it for single frames and
+    FSB_COLOUR_SLICE cuts the colour pass into slices of the record lists.  Same frames as the oracle whatever the path:
+    both filters, both sentinels, smoothing, ragged widths, ragged series in a batch, empty and one-sample series."""
     col, hgt = fbm1024
     mp = gpu_ctx.upload_map(col, hgt)
-    monkeypatch.setenv("FSB_SEGMENTS", str(segments))      # read per call (fsb_api.c)
+    monkeypatch.setenv("FSB_COLS_MIN_WARPS", "0")              # read per call (fsb_api.c)
+    monkeypatch.setenv("FSB_COLOUR_SLICE", str(slice_len))
+    n0 = gpu_ctx.launch_count
+    check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*POSES[0], SKY), fsb.default_params(), 300, 417)
+    assert gpu_ctx.launch_count - n0 == 4                      # set-up, march, colour, expand
     for filt in (1, 0):
         for sentinel in (0, 1):
             prm = fsb.default_params(filter=filt, sentinel=sentinel)
@@ -570,7 +574,7 @@ def test_depth_series_split_over_warps(fsb, oracle, gpu_ctx, fbm1024, monkeypatc
         check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 257, 95)
     prm = fsb.default_params()
     cam = fsb.Camera(512.37, 512.73, 180, 2.2, 40, 300, 1.2, SKY)
-    for dist in (0.0004, 0.001, 0.6, 2.0, 30.0):            # n_z = 0, 1, 35, 63, 245: fewer blocks than segments
+    for dist in (0.0004, 0.001, 0.6, 2.0, 30.0):            # n_z = 0, 1, 35, 63, 245
         cam.distance = dist
         check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, 64, 48)
     cams = camera_path(fsb, 1024, 5, 700)
@@ -578,8 +582,24 @@ def test_depth_series_split_over_warps(fsb, oracle, gpu_ctx, fbm1024, monkeypatc
     frames = gpu_ctx.render_batch(cams, prm, mp, 135, 240)
     for cam, got in zip(cams, frames):
         assert np.array_equal(got, oracle.render(ocam(oracle, cam), oprm(oracle, prm), col, hgt & 0xFF, 135, 240))
-    # tests variant (z0 = 1, sky sentinel, nearest) and a tall narrow frame
+    # tests variant (z0 = 1, sky sentinel, nearest), a tall narrow frame, and the tallest frame the library takes
     check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(512, 800, 78, 0, 100, 800, 1, SKY), fsb.tests_variant_params(), 400, 33)
+    check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(512.37, 512.73, 150, 2.2, 9000, 700, 1.2, SKY), fsb.default_params(), 32768, 40)
+    mp.free()
+
+
+def test_batch_paths_agree(fsb, oracle, gpu_ctx, fbm1024):
+    """A batch large enough for the column-parallel march (default path) against the lanes-over-depth march
+    (FSB_FLAG_MARCH_Z) and the oracle, frame by frame."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    cams = camera_path(fsb, 1024, 96, 900)
+    a = gpu_ctx.render_batch(cams, fsb.default_params(), mp, 270, 480)
+    b = gpu_ctx.render_batch(cams, fsb.default_params(flags=fsb.FLAG_MARCH_Z), mp, 270, 480)
+    assert np.array_equal(a, b)
+    for i in (0, 31, 32, 63, 95):
+        want = oracle.render(ocam(oracle, cams[i]), oprm(oracle, fsb.default_params()), col, hgt & 0xFF, 270, 480)
+        assert np.array_equal(a[i], want), i
     mp.free()
 
 
