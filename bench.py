@@ -182,35 +182,50 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
-    """dram bytes per launch of the march kernel from the committed ncu capture, if any (profiles/traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(workload)
-    return None
-
-
 # ------------------------------------------------------------------------------------------------
+def make_config(wl, world, P, nz, m):
+    """The workload description both arms print (identical keys and values: the driver compares them)."""
+    w, h = wl["w"], wl["h"]
+    return {"workload": wl["name"], "frame": [w, h], "map": m, "distance": wl["dist"], "n_z": nz, "filter": "bilinear",
+            "poses_per_gpu_per_step": P, "global_poses_per_step": P * world,
+            "occlusion_bound": "on (default path; frames bit-identical to the full evaluation, see roofline)",
+            "parallelism": "frame-parallel x%d (pose i -> GPU i mod N), maps replicated, no collective" % world,
+            "l2": "256 MiB scratch write between timed steps (flush); each step also streams %.1f GB of frames through "
+                  "the 126 MB L2; the %d MiB packed map is L2-resident by design" % (P * w * h * 4 / 1e9, m * m * 4 >> 20)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count()
+
+
 def run_reference(args, wl):
-    """CPU arm: the oracle (C restatement of the reference) on all host threads, rank 0 only."""
+    """CPU arm: the oracle (C restatement of the reference) on all host threads, rank 0 only.  Loads nothing of the
+    product: the terrain generator source is also compiled into the oracle library (oracle/Makefile)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    import futspace_b200 as F   # terrain generator + z-series only (host functions, no GPU)
-    m, w, h, dist = wl["map"], wl["w"], wl["h"], wl["dist"]
-    col, hgt = F.terrain_fbm(m)
+    m, w, h, dist = args.map or wl["map"], wl["w"], wl["h"], wl["dist"]
+    world = max(1, args.gpus)
+    P = args.poses or wl["poses"]
+    col, hgt = O.terrain_fbm(m)
     prm = O.default_params()
+    nz = len(O.get_zs(prm.delta, dist, prm.z0))
     n_ref = wl["ref_poses"]
-    total = wl["poses"] * max(1, args.gpus)
-    cores = os.cpu_count()
+    total = P * world
+    # torchrun exports OMP_NUM_THREADS=1: the thread count is passed explicitly (num_threads clause in the oracle)
+    threads = host_threads()
+
     # the sample: n_ref poses evenly spaced over the global path, a different offset each step
     def step(s):
         idx = [((s * 7 + j * (total // n_ref)) % total) for j in range(n_ref)]
         for i in idx:
             cam = camera_path(O, hgt, m, total, i, 1, h, dist)[0]
-            O.render(cam, prm, col, hgt, h, w, eval_all_colors=True, nthreads=0)
+            O.render(cam, prm, col, hgt, h, w, eval_all_colors=True, nthreads=threads)
     for s in range(args.warmup):
         step(s)
     t0 = time.perf_counter()
@@ -222,12 +237,12 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "frame": [w, h], "map": m, "distance": dist, "filter": "bilinear",
-                   "poses_per_step": n_ref},
-        "mpixel_per_s": fps * w * h / 1e6,
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "cpu_model": cpu_model(), "kind": "port",
+        "config": make_config(wl, world, P, nz, m),
+        "mpixel_per_s": fps * w * h / 1e6, "threads": threads,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "cpu_model": cpu_model(), "kind": "port",
                          "sample": "%d of the %d path poses per step, C restatement of the reference (oracle/), "
-                                   "OpenMP over columns, colour filter evaluated for every sample" % (n_ref, total)},
+                                   "OpenMP over columns on %d threads, colour filter evaluated for every sample"
+                                   % (n_ref, total, threads)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -249,9 +264,222 @@ def time_device_steps(torch, ctx, st, fn, steps, flush):
     return [a.elapsed_time(b) for a, b in evs]
 
 
+def ncu_rates(workload):
+    """Per-pose warp-instruction counts, L2 sectors and DRAM bytes of each kernel from the committed ncu captures
+    (profiles/r2_ncu_rates.json, written by tools/ncu_rates.py from profiles/r2_*_ncu.txt)."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_rates.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(workload)
+    return None
+
+
+SM_COUNT, SCHEDULERS = 148, 4
+TLD4_CYCLES_PER_SM = 8.2   # measured: tools/scratch/tex_rate.cu, profiles/r2_tex_rate.txt (0.122 warp-tld4 / clk / SM)
+
+
+def measure(torch, F, O, ctx, st, flush, wl, wl_key, m, col, hgt, mp, P, steps, warmup, rank, world, barrier, max_over_ranks,
+            local, do_clocks):
+    """One workload: device-resident throughput (`value`), the same with every sample evaluated, per-kernel split and
+    bounds, parity of frames of the timed batch against the oracle, e2e through host buffers, single-frame latency."""
+    import numpy as np
+    w, h, dst = wl["w"], wl["h"], wl["dist"]
+    prm = F.default_params()
+    nz = n_z_of(F, prm, dst)
+    total = P * world
+    cams = camera_path(F, hgt, m, total, rank, P, h, dst, stride=world)   # pose i -> rank i mod N (shard.pose_interleave)
+    cam_arr = (F.Camera * P)(*cams)
+    frame_bytes = w * h * 4
+    out_dev = ctx.device_malloc(P * frame_bytes)
+
+    def step_dev():
+        ctx.render_batch_device(cam_arr, prm, mp, h, w, out_dev)
+
+    # ---- value: device-resident frames ----
+    for _ in range(warmup):
+        step_dev()
+    barrier()
+    ctx.sync()
+    sampler = ClockSampler(local) if do_clocks else None
+    if sampler:
+        sampler.start()
+    n0 = ctx.launch_count
+    ms = time_device_steps(torch, ctx, st, step_dev, steps, flush)
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop() if sampler else None
+    barrier()
+    total_ms = max_over_ranks(sum(ms))
+    value = total * steps / (total_ms / 1e3)
+
+    # ---- parity of the timed batch: frames of the LAST timed step, straight from out_dev, against the oracle ----
+    rng = np.random.default_rng(1234 + rank)
+    idx = sorted({0, 1, P // 2 - 1, P // 2, P - 2, P - 1, *[int(x) for x in rng.integers(0, P, size=4)]} & set(range(P)))
+    oprm = O.default_params()
+    bad = 0
+    for i in idx:
+        got = ctx.download(out_dev + i * frame_bytes, (h, w))
+        c = cams[i]
+        want = O.render(O.Camera(c.x, c.y, c.height, c.angle, c.horizon, c.distance, c.fov, c.sky_color), oprm, col, hgt,
+                        h, w, nthreads=host_threads())
+        bad += int((got != want).sum())
+    bad = int(max_over_ranks(float(bad)))
+    parity = {"frames": len(idx), "differing_pixels": bad, "pose_indices": idx,
+              "what": "frames of the last timed step, read back from the timed output buffer, bit-compared with the oracle"}
+
+    # ---- the same steps with every depth sample evaluated (FSB_FLAG_NO_CULL: no occlusion bound, no row-0 exit) ----
+    prm_all = F.default_params(flags=F.FLAG_NO_CULL)
+
+    def step_dev_all():
+        ctx.render_batch_device(cam_arr, prm_all, mp, h, w, out_dev)
+
+    for _ in range(3):
+        step_dev_all()
+    barrier()
+    n_all = max(3, min(steps, 20))
+    ms_all = time_device_steps(torch, ctx, st, step_dev_all, n_all, flush)
+    value_all = total * n_all / (max_over_ranks(sum(ms_all)) / 1e3)
+
+    # ---- per-kernel split and counters, default path and full evaluation ----
+    def profile(fn):
+        ctx.set_profiling(True)
+        fn()
+        ctx.get_profile()
+        ctx.get_counters()
+        for _ in range(2):
+            fn()
+        prof = ctx.get_profile()
+        chunks, records = ctx.get_counters()
+        ctx.set_profiling(False)
+        return prof, chunks / 2.0, records / 2.0
+
+    prof_cull, chunks_cull, records = profile(step_dev)
+    prof_full, chunks_full, _ = profile(step_dev_all)
+    all_chunks = float(P) * w * ((nz + 31) // 32)
+    march_ms, march_n = prof_full["march"]
+    poses_per_launch = 2.0 * P / march_n
+    gather_bytes = 4.0 * 4 * w * nz                    # 4 taps x 4 B packed texel per sample (SURVEY 8d)
+    frame_alg = 4.0 * w * h
+    peak, peak_src = measured_peaks()
+    achieved = gather_bytes * poses_per_launch / (march_ms / march_n * 1e-3) / 1e9
+    rates = ncu_rates(wl_key)
+    f_sm = (clocks or {}).get("sm_mhz") or 1965.0
+    slots_per_ms = SM_COUNT * SCHEDULERS * f_sm * 1e3          # warp-instruction issue slots per millisecond
+    kern_cull = {k: v[0] / 2 for k, v in prof_cull.items()}
+    kern_full = {k: v[0] / 2 for k, v in prof_full.items()}
+    kernels = {}
+    for name in ("march", "colour", "expand"):
+        e = {"ms_per_step": kern_cull[name], "ms_per_step_full_evaluation": kern_full[name]}
+        if rates and name in rates and kern_cull[name] > 1e-4:
+            r = rates[name]
+            e["warp_instructions_per_pose_ncu"] = r["inst_per_pose"]
+            # march instructions scale with the chunks evaluated, the others do not depend on the bound
+            scale = (chunks_cull / max(chunks_full, 1.0)) / r.get("chunks_frac_in_capture", 1.0) if name == "march" else 1.0
+            e["issue_slot_frac"] = r["inst_per_pose"] * scale * P / (slots_per_ms * kern_cull[name])
+            e["dram_bytes_per_pose_ncu"] = r["dram_bytes_per_pose"]
+            if name == "march":
+                e["l2_sectors_per_sample_ncu"] = r["lts_tex_read_sectors_per_pose"] / (32.0 * chunks_cull / P)
+        kernels[name] = e
+    # march: texture-pipe bound -- one tld4 per 32 samples, 8.2 cycles of the SM's texture pipe each
+    kernels["march"]["tex_pipe_frac"] = chunks_cull * 32 * TLD4_CYCLES_PER_SM / (SM_COUNT * f_sm * 1e3 * kern_cull["march"])
+    kernels["march"]["tex_pipe_frac_full_evaluation"] = (chunks_full * 32 * TLD4_CYCLES_PER_SM /
+                                                         (SM_COUNT * f_sm * 1e3 * kern_full["march"]))
+    # expand: HBM bound -- the frame must be written once
+    kernels["expand"]["hbm_frac_frame_bytes_only"] = frame_alg * P / (kern_cull["expand"] * 1e-3) / 1e9 / peak
+    if rates and "expand" in rates:
+        kernels["expand"]["hbm_frac_ncu_traffic"] = (rates["expand"]["dram_bytes_per_pose"] * P /
+                                                     (kern_cull["expand"] * 1e-3) / 1e9 / peak)
+    tr = rates["march"]["dram_bytes_per_pose"] * poses_per_launch if rates and "march" in rates else None
+    share = march_ms / sum(v[0] for v in prof_full.values())
+    roofline = {"bound": "hbm", "kernel": "fsb_marchc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": gather_bytes * poses_per_launch,
+                "launch_ms": march_ms / march_n, "kernel_share_of_step": share,
+                "mode": "FSB_FLAG_NO_CULL: neither the occlusion bound nor the row-0 exit ends a column early",
+                "chunks_evaluated_of_all": chunks_full / all_chunks,
+                "note": "HBM is the bound the contract names, not the limiter: the 16 B per depth sample of SURVEY 8d are "
+                        "served by the texture unit from L1/L2 (traffic = what ncu saw cross DRAM).  What binds the march "
+                        "is the texture pipe (one tld4 per 32 samples at 8.2 cycles per SM: kernels.march.tex_pipe_frac) and "
+                        "instruction issue (kernels.march.issue_slot_frac); the frame store binds expand (hbm_frac_*).",
+                "default_path": {"march_launch_ms": prof_cull["march"][0] / prof_cull["march"][1],
+                                 "chunks_evaluated_of_all": chunks_cull / all_chunks,
+                                 "records_per_frame": records / P}}
+    step_alg = (gather_bytes + frame_alg) * P
+    full_ms = sum(kern_full.values())
+    roofline_step = {"achieved": step_alg / (full_ms * 1e-3) / 1e9, "unit": "GB/s per GPU (full evaluation)",
+                     "frac": step_alg / (full_ms * 1e-3) / 1e9 / peak,
+                     "algorithmic_bytes_per_step_per_gpu": step_alg,
+                     "hbm_floor_ms_per_step": frame_alg * P / peak / 1e6,
+                     "kernel_ms_per_step": kern_full}
+
+    # ---- e2e: host frames through fsb_render_batch (pinned), copies inside the timed region ----
+    host = ctx.host_malloc(P * frame_bytes)
+
+    def step_e2e():
+        ctx.render_batch(cam_arr, prm, mp, h, w, out=host)
+
+    for _ in range(max(1, min(warmup, 2))):
+        step_e2e()
+    barrier()
+    e_steps = max(1, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        step_e2e()
+    ctx.sync()
+    e_dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": total * e_steps / e_dt, "unit": "frames/s", "h2d_bytes_per_step": 64 * P,
+           "d2h_bytes_per_step": P * frame_bytes, "steps": e_steps, "ms_per_step": 1e3 * e_dt / e_steps,
+           "d2h_gb_per_s_aggregate": total * frame_bytes * e_steps / e_dt / 1e9,
+           "api": "fsb_render_batch (pinned host frames; pose constants H2D + frames D2H inside the timed region)"}
+    # the host frames of the last e2e step are checked too (first and last pose)
+    import ctypes
+    hv = np.ctypeslib.as_array(ctypes.cast(host, ctypes.POINTER(ctypes.c_uint32)), shape=(P, h, w))
+    e_bad = 0
+    for i in (0, P - 1):
+        c = cams[i]
+        want = O.render(O.Camera(c.x, c.y, c.height, c.angle, c.horizon, c.distance, c.fov, c.sky_color), oprm, col, hgt,
+                        h, w, nthreads=host_threads())
+        e_bad += int((hv[i] != want).sum())
+    e2e["parity_checked"] = {"frames": 2, "differing_pixels": e_bad}
+
+    # ---- single frames: the reference's actual use, one frame per SDL iteration (c/interactive.c:111) ----
+    single = F.Camera(m / 2 + 0.37, m / 2 + 0.73, max(160.0, float(hgt[m // 2, m // 2]) + 20.0), 2.2, 0.3 * h, dst, 1.2, SKY)
+
+    def one_frame():
+        ctx.render_device(single, prm, mp, h, w, out_dev)
+
+    one_frame()
+    ms1 = time_device_steps(torch, ctx, st, one_frame, 20, flush)
+    single_us = {"device_cold_l2": 1e3 * sorted(ms1)[len(ms1) // 2]}   # median; L2 flushed before each frame
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(50):
+        one_frame()
+    e1.record(st)
+    e1.synchronize()
+    single_us["device_back_to_back"] = 1e3 * e0.elapsed_time(e1) / 50   # map L2-resident, launches queued
+    hostbuf = np.zeros((h, w), np.uint32)
+    ctx.host_register(hostbuf)
+    ctx.render(single, prm, mp, h, w, out=hostbuf)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ctx.render(single, prm, mp, h, w, out=hostbuf)     # blocking: frame in the registered host buffer on return
+    single_us["fsb_render_registered_host_buffer"] = 1e6 * (time.perf_counter() - t0) / 20
+    ctx.host_unregister(hostbuf)
+
+    res = {"value": value, "ms_per_step": total_ms / steps, "mpixel_per_s": value * w * h / 1e6,
+           "value_full_evaluation": value_all, "config": make_config(wl, world, P, nz, m), "clocks": clocks, "e2e": e2e,
+           "gpu_launches": launches, "roofline": roofline, "roofline_step": roofline_step, "kernels": kernels,
+           "parity_checked": parity, "single_frame_us": single_us}
+    ctx.host_free(host)
+    ctx.device_free(out_dev)
+    return res, cams, cam_arr
+
+
 def run_ours(args, wl):
     import torch
     import futspace_b200 as F
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O   # the checker of parity_checked and the cpu_baseline leg; never on the measured path
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -283,125 +511,15 @@ def run_ours(args, wl):
     col, hgt = F.terrain_fbm(m)
     ctx = F.Context(local)
     mp = ctx.upload_map(col, hgt)
-    prm = F.default_params()
-    nz = n_z_of(F, prm, dst)
-    total = P * world
-    cams = camera_path(F, hgt, m, total, rank, P, h, dst, stride=world)   # pose i -> rank i mod N (shard.pose_interleave)
-    cam_arr = (F.Camera * P)(*cams)
-    frame_bytes = w * h * 4
     st = torch.cuda.ExternalStream(ctx.stream)
     flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    out_dev = ctx.device_malloc(P * frame_bytes)
+    res, cams, cam_arr = measure(torch, F, O, ctx, st, flush, wl, args.workload, m, col, hgt, mp, P, args.steps, args.warmup,
+                                 rank, world, barrier, max_over_ranks, local, True)
+    total = P * world
+    prm = F.default_params()
+    out_dev = ctx.device_malloc(P * w * h * 4)
 
-    def step_dev():
-        ctx.render_batch_device(cam_arr, prm, mp, h, w, out_dev)
-
-    # ---- value: device-resident frames ----
-    for _ in range(args.warmup):
-        step_dev()
-    barrier()
-    ctx.sync()
-    sampler = ClockSampler(local)
-    sampler.start()
-    n0 = ctx.launch_count
-    ms = time_device_steps(torch, ctx, st, step_dev, args.steps, flush)
-    launches = ctx.launch_count - n0
-    clocks = sampler.stop()
-    barrier()
-    total_ms = max_over_ranks(sum(ms))
-    value = total * args.steps / (total_ms / 1e3)
-
-    # ---- the same steps with the occlusion bound off (every depth sample evaluated), for transparency ----
-    prm_all = F.default_params(flags=F.FLAG_NO_CULL)
-
-    def step_dev_all():
-        ctx.render_batch_device(cam_arr, prm_all, mp, h, w, out_dev)
-
-    for _ in range(3):
-        step_dev_all()
-    barrier()
-    n_all = max(3, min(args.steps, 20))
-    ms_all = time_device_steps(torch, ctx, st, step_dev_all, n_all, flush)
-    value_all = total * n_all / (max_over_ranks(sum(ms_all)) / 1e3)
-
-    # ---- per-kernel share + roofline of the dominant kernel (march) ----
-    # The roofline is taken with the occlusion bound switched off (FSB_FLAG_NO_CULL): every depth sample is
-    # fetched and evaluated, so the algorithmic bytes are really moved.  The default path (`value`) skips the
-    # chunks the bound proves hidden; its kernel times and the fraction of chunks it evaluates are reported too.
-    ctx.set_profiling(True)
-    step_dev()
-    ctx.get_profile()
-    ctx.get_counters()
-    for _ in range(2):
-        step_dev()
-    prof_cull = ctx.get_profile()
-    chunks_eval, records = ctx.get_counters()
-    prm_full = F.default_params(flags=F.FLAG_NO_CULL)
-
-    def step_full():
-        ctx.render_batch_device(cam_arr, prm_full, mp, h, w, out_dev)
-
-    step_full()
-    ctx.get_profile()
-    ctx.get_counters()
-    for _ in range(2):
-        step_full()
-    prof = ctx.get_profile()
-    chunks_full, _ = ctx.get_counters()
-    ctx.set_profiling(False)
-    march_ms, march_n = prof["march"]
-    expand_ms, expand_n = prof["expand"]
-    setup_ms, setup_n = prof["setup"]
-    poses_per_launch = 2.0 * P / march_n
-    gather_bytes = 4.0 * 4 * w * nz                    # 4 taps x 4 B packed texel per sample
-    frame_alg = 4.0 * w * h
-    peak, peak_src = measured_peaks()
-    achieved = gather_bytes * poses_per_launch / (march_ms / march_n * 1e-3) / 1e9
-    tr = ncu_traffic(args.workload)
-    tr = tr["dram_bytes_per_pose"] * poses_per_launch if tr else None
-    roofline = {"bound": "hbm", "kernel": "fsb_march_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": gather_bytes * poses_per_launch,
-                "launch_ms": march_ms / march_n,
-                "kernel_share_of_step": march_ms / (march_ms + expand_ms + setup_ms),
-                "mode": "occlusion bound off (FSB_FLAG_NO_CULL): all W*n_z samples evaluated",
-                "note": "frac can exceed 1: the algorithmic gather bytes (16 B per depth sample) are served from L1/L2 -- "
-                        "neighbouring samples share 32-byte sectors of the 2-byte height texture -- so HBM is the nominal "
-                        "bound the contract asks for, not the limiter; ncu (profiles/r1_end_march_*) shows the kernel "
-                        "issue-bound: 76 % issue-active, XU pipe 60 %, DRAM 3.5 %",
-                "default_path": {"march_launch_ms": prof_cull["march"][0] / prof_cull["march"][1],
-                                 "chunks_evaluated_frac": chunks_eval / max(1, chunks_full),
-                                 "records_per_frame": records / (2.0 * P),
-                                 "kernel_ms_per_step": {k: v[0] / 2 for k, v in prof_cull.items()}}}
-    step_alg = (gather_bytes + frame_alg) * P
-    full_ms = (march_ms + expand_ms + setup_ms) / 2
-    roofline_step = {"achieved": step_alg / (full_ms * 1e-3) / 1e9, "unit": "GB/s per GPU (occlusion bound off)",
-                     "frac": step_alg / (full_ms * 1e-3) / 1e9 / peak,
-                     "algorithmic_bytes_per_step_per_gpu": step_alg,
-                     "kernel_ms_per_step": {"setup": setup_ms / 2, "march": march_ms / 2, "expand": expand_ms / 2}}
-
-    # ---- e2e: host frames through fsb_render_batch (pinned), copies inside the timed region ----
-    host = ctx.host_malloc(P * frame_bytes)
-
-    def step_e2e():
-        ctx.render_batch(cam_arr, prm, mp, h, w, out=host)
-
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    barrier()
-    e_steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        step_e2e()
-    ctx.sync()
-    e_dt = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = total * e_steps / e_dt
-    e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 64 * P, "d2h_bytes_per_step": P * frame_bytes,
-           "steps": e_steps, "ms_per_step": 1e3 * e_dt / e_steps,
-           "api": "fsb_render_batch (pinned host frames; pose constants H2D + frames D2H inside the timed region)"}
-
-    # ---- secondary runs: other renderer variants on the same path, single-frame latency ----
+    # ---- secondary runs: other renderer variants on the same path ----
     def timed(prm_x, n_steps=5):
         def f():
             ctx.render_batch_device(cam_arr, prm_x, mp, h, w, out_dev)
@@ -413,23 +531,9 @@ def run_ours(args, wl):
         "tests_variant_frames_per_s": timed(F.tests_variant_params()),   # z0 = 1, d = 0.005, nearest, sky sentinel, 240
         "smoothing_on_frames_per_s": timed(F.default_params(flags=F.FLAG_SMOOTHING)),
         "nearest_frames_per_s": timed(F.default_params(filter=0)),
+        # A/B: the lanes-over-depth march (round 1; today the path of single frames and small batches) on the same batch
+        "lanes_over_depth_march_frames_per_s": timed(F.default_params(flags=F.FLAG_MARCH_Z)),
     }
-    single = F.Camera(m / 2 + 0.37, m / 2 + 0.73, max(160.0, float(hgt[m // 2, m // 2]) + 20.0), 2.2, 0.3 * h, dst, 1.2, SKY)
-
-    def one_frame():
-        ctx.render_device(single, prm, mp, h, w, out_dev)
-
-    one_frame()
-    ms1 = time_device_steps(torch, ctx, st, one_frame, 20, flush)
-    secondary["single_frame_cold_l2_us"] = 1e3 * sorted(ms1)[len(ms1) // 2]   # median; 3 launches, L2 flushed before each
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    for _ in range(50):
-        one_frame()
-    e1.record(st)
-    e1.synchronize()
-    secondary["single_frame_back_to_back_us"] = 1e3 * e0.elapsed_time(e1) / 50   # map L2-resident, launches queued
-
     if args.workload == "cfg1":
         # BASELINE config 1 names the reference's own converted map pair: C1W / D1 (committed copy, tests/golden/)
         import numpy as np
@@ -448,55 +552,62 @@ def run_ours(args, wl):
             ms2 = time_device_steps(torch, ctx, st, f2, 5, flush)
             secondary["c1w_d1_map_frames_per_s"] = total * 5 / (max_over_ranks(sum(ms2)) / 1e3)
             mp2.free()
+    ctx.device_free(out_dev)
     extra = {"secondary": secondary}
     cpu = None
     if rank == 0:
         extra["l2_stream_gbs"] = ctx.l2_stream_gbs()
         extra["l2_gather_gsectors"] = ctx.l2_gather_gsectors()
-        taps_per_s = 4.0 * w * nz * poses_per_launch / (march_ms / march_n * 1e-3)
-        extra["l2_gather_roofline_frac"] = taps_per_s / (extra["l2_gather_gsectors"] * 1e9)
         if world == 1 and not args.no_cpu:
-            cpu = cpu_baseline(F, wl, col, hgt, total)
-    ctx.host_free(host)
-    ctx.device_free(out_dev)
+            cpu = cpu_baseline(O, wl, col, hgt, total)
     mp.free()
+
+    # ---- the north-star target config rides in the same line: 3840x2160, 4096^2 map, distance 4000 ----
+    configs = {}
+    if args.workload == "1080p" and not args.no_4k:
+        wl4 = WORKLOADS["4k"]
+        col4, hgt4 = F.terrain_fbm(wl4["map"])
+        mp4 = ctx.upload_map(col4, hgt4)
+        r4, _, _ = measure(torch, F, O, ctx, st, flush, wl4, "4k", wl4["map"], col4, hgt4, mp4, wl4["poses"],
+                           max(3, min(args.steps, 30)), args.warmup, rank, world, barrier, max_over_ranks, local, True)
+        mp4.free()
+        configs["4k"] = r4
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
     if rank != 0:
         return
     out = {
-        "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": "frames/s", "value": res["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "frame": [w, h], "map": m, "distance": dst, "n_z": nz,
-                   "filter": "bilinear", "poses_per_gpu_per_step": P, "global_poses_per_step": total,
-                   "occlusion_bound": "on (default path; frames bit-identical to the full evaluation, see roofline.default_path)",
-                   "parallelism": "frame-parallel x%d (pose i -> GPU i mod N), maps replicated, no collective" % world,
-                   "l2": "256 MiB scratch write between timed steps (flush); each step also streams %.1f GB of "
-                         "frames through the 126 MB L2; the %d MiB packed map is L2-resident by design"
-                         % (P * frame_bytes / 1e9, m * m * 4 >> 20)},
-        "mpixel_per_s": value * w * h / 1e6,
-        "value_full_evaluation": value_all,   # occlusion bound off: all W*n_z samples fetched and evaluated
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_step": roofline_step,
-        "cpu_baseline": cpu,
     }
+    out.update({k: v for k, v in res.items() if k not in ("value", "ms_per_step")})
+    out["cpu_baseline"] = cpu
+    out["configs"] = configs
     out.update(extra)
     print(json.dumps(out), flush=True)
 
 
 def run_colsplit(args, wl):
-    """Column-split mode: rank r renders columns [b[r], b[r+1]) of ONE frame.  Two ways to assemble it on
-    rank 0 are timed: (a) fused -- every rank's expand kernel stores straight into rank 0's frame through a CUDA-IPC
-    peer mapping (NVLink), no separate collective; (b) each rank renders a private slab and NCCL gathers them."""
+    """Column-split mode (BASELINE config 5): rank r renders columns [b[r], b[r+1]) of ONE frame.  Three ways
+    to assemble it are timed: (a) fused -- every rank's expand kernel stores straight into rank 0's device frame through a
+    CUDA-IPC peer mapping (NVLink), no separate collective; (b) private slabs + NCCL gather to rank 0; (c) host frame --
+    every rank copies its slab into ONE shared page-locked host frame over its own PCIe link (fsb_render_columns).
+    The assembled frames are compared with the ORACLE's render of the whole frame on the same map."""
+    import ctypes
+    from multiprocessing import shared_memory
     import numpy as np
     import torch
     import futspace_b200 as F
     from futspace_b200.shard import column_bounds, gather_columns
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    pin_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -509,10 +620,17 @@ def run_colsplit(args, wl):
     prm = F.default_params()
     nz = n_z_of(F, prm, dst)
     cam = F.Camera(m / 2 + 0.37, m / 2 + 0.73, max(160.0, float(hgt[m // 2, m // 2]) + 20.0), 2.2, 0.3 * h, dst, 1.2, SKY)
-    del col
     b = column_bounds(w, world)
     c0, c1 = b[rank], b[rank + 1]
     st = torch.cuda.ExternalStream(ctx.stream)
+    # the oracle's frame (rank 0; before the maps are dropped): the whole 7680x4320 frame on the same 16384^2 map
+    want = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        want = O.render(O.Camera(cam.x, cam.y, cam.height, cam.angle, cam.horizon, cam.distance, cam.fov, cam.sky_color),
+                        O.default_params(), col, hgt, h, w, nthreads=host_threads())
+        oracle_s = time.perf_counter() - t0
+    del col
 
     def barrier():
         ctx.sync()
@@ -558,12 +676,69 @@ def run_colsplit(args, wl):
     launches = ctx.launch_count - n0
     clocks = sampler.stop()
     barrier()
-    ok = None
-    if rank == 0:   # the assembled frame equals a single-GPU render of the whole frame
-        ref = ctx.device_malloc(h * w * 4)
-        ctx.render_device(cam, prm, mp, h, w, ref)
-        ok = bool(np.array_equal(ctx.download(frame, (h, w)), ctx.download(ref, (h, w))))
-        ctx.device_free(ref)
+    parity = None
+    own_ms = None
+    if rank == 0:
+        got = ctx.download(frame, (h, w))
+        parity = {"frames": 1, "differing_pixels": int((got != want).sum()), "oracle_seconds": oracle_s,
+                  "what": "the frame assembled in rank 0's device memory from all slabs against the oracle's render of the "
+                          "whole frame on the same %d^2 map" % m}
+    own = timed(lambda: ctx.render_columns_device(cam, prm, mp, h, w, c0, c1, (frame if rank == 0 else base) + 4 * c0, w), 3)
+    own_ms = sum(own) / len(own)
+
+    # (a') e2e of the device-assembled frame: rank 0 reads the whole frame back over its one PCIe link
+    e2e_dev = None
+    hostfull = ctx.host_malloc(h * w * 4) if rank == 0 else None
+    tt = []
+    for _ in range(max(1, min(args.steps, 5))):
+        barrier()
+        t0 = time.perf_counter()
+        step_fused()
+        barrier()
+        if rank == 0:
+            ctx.copy_to_host(hostfull, frame, h * w * 4)
+            ctx.sync()
+        tt.append(1e3 * (time.perf_counter() - t0))
+    e2e_dev = sum(reduce_max(tt)) / len(tt)
+
+    # (c) host frame: every rank DMAs its slab into ONE shared page-locked host frame over its own PCIe link
+    shm = None
+    name = [None]
+    if rank == 0:
+        shm = shared_memory.SharedMemory(create=True, size=h * w * 4)
+        name[0] = shm.name
+    if dist is not None:
+        dist.broadcast_object_list(name, src=0)
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=name[0])
+    hostframe = np.ndarray((h, w), dtype=np.uint32, buffer=shm.buf)
+    if rank == 0:
+        hostframe[:] = 0
+    barrier()
+    ctx.host_register_ptr(hostframe.ctypes.data, h * w * 4)
+
+    def step_host():
+        ctx.render_columns(cam, prm, mp, h, w, c0, c1, hostframe.ctypes.data + 4 * c0, w)
+
+    for _ in range(2):
+        step_host()
+    tt = []
+    for _ in range(max(1, min(args.steps, 10))):
+        barrier()
+        t0 = time.perf_counter()
+        step_host()
+        barrier()                      # the frame is complete when every rank's slab has landed
+        tt.append(1e3 * (time.perf_counter() - t0))
+    host_ms = sum(reduce_max(tt)) / len(tt)
+    host_parity = None
+    if rank == 0:
+        host_parity = {"frames": 1, "differing_pixels": int((hostframe != want).sum())}
+    barrier()
+    ctx.host_unregister_ptr(hostframe.ctypes.data)
+    del hostframe
+    shm.close()
+    if rank == 0:
+        shm.unlink()
 
     # (b) private slabs + NCCL gather to rank 0
     gather_ms = None
@@ -593,6 +768,7 @@ def run_colsplit(args, wl):
         ms = sum(fused) / len(fused)
         peak, peak_src = measured_peaks()
         alg = 4.0 * 4 * w * nz + 4.0 * w * h
+        ingest = (w - (b[1] - b[0])) * h * 4.0     # bytes the other ranks push into rank 0's frame over NVLink
         print(json.dumps({
             "metric": "frames/s", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -603,11 +779,22 @@ def run_colsplit(args, wl):
                        "l2": "single frame per step; the touched map footprint (~77 MB packed at distance 4000) and the "
                              "133 MB frame exceed what stays resident between steps"},
             "mpixel_per_s": w * h / ms / 1e3, "clocks": clocks, "gpu_launches": launches,
-            "frame_matches_single_gpu": ok,
+            "parity_checked": parity,
             "fused_peer_store_ms_per_frame": ms, "nccl_gather_ms_per_frame": gather_ms,
-            "roofline_step": {"achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s (algorithmic, whole frame)", "frac": alg / (ms * 1e-3) / 1e9 / peak / world,
-                              "peak_source": peak_src},
-            "e2e": None, "cpu_baseline": None,
+            "slab_render_ms_rank_max": own_ms,
+            "nvlink_ingest_gb_per_s_rank0": ingest / (ms * 1e-3) / 1e9 if world > 1 else None,
+            "limiter": ("one GPU renders the whole frame" if world == 1 else
+                        "rank 0's NVLink ingest of %.0f MB of peer stores (%.0f GB/s of 900 nominal / 770 measured per "
+                        "direction) plus the fixed launch chain of a slab" % (ingest / 1e6, ingest / (ms * 1e-3) / 1e9)),
+            "roofline_step": {"achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s (algorithmic, whole frame)",
+                              "frac": alg / (ms * 1e-3) / 1e9 / peak / world, "peak_source": peak_src},
+            "e2e": {"value": 1e3 / host_ms, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": h * w * 4,
+                    "ms_per_step": host_ms, "parity_checked": host_parity,
+                    "api": "fsb_render_columns on every rank into one shared page-locked host frame (each GPU's PCIe link "
+                           "carries its own slab); wall clock between barriers",
+                    "device_assembled_then_d2h_ms": e2e_dev,
+                    "d2h_gb_per_s_aggregate": h * w * 4 / (host_ms * 1e-3) / 1e9},
+            "cpu_baseline": None,
         }), flush=True)
     mp.free()
     ctx.close()
@@ -625,19 +812,18 @@ def cpu_model():
     return "unknown"
 
 
-def cpu_baseline(F, wl, col, hgt, total):
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
+def cpu_baseline(O, wl, col, hgt, total):
     m, w, h, dst = wl["map"], wl["w"], wl["h"], wl["dist"]
     prm = O.default_params()
+    threads = host_threads()
     cam0 = camera_path(O, hgt, m, total, 0, 1, h, dst)[0]
-    O.render(cam0, prm, col, hgt, h, w, eval_all_colors=True, nthreads=0)   # warm-up
+    O.render(cam0, prm, col, hgt, h, w, eval_all_colors=True, nthreads=threads)   # warm-up
     # bounded sample: poses spread over the path (stride 37 is coprime to the path length) until ~12 s of CPU work
     t0 = time.perf_counter()
     n = 0
     while n < total and time.perf_counter() - t0 < 12.0:
         i = (n * 37) % total
-        O.render(camera_path(O, hgt, m, total, i, 1, h, dst)[0], prm, col, hgt, h, w, eval_all_colors=True, nthreads=0)
+        O.render(camera_path(O, hgt, m, total, i, 1, h, dst)[0], prm, col, hgt, h, w, eval_all_colors=True, nthreads=threads)
         n += 1
     dt = time.perf_counter() - t0
     # the `futhark c` (sequential backend) analogue: the same code on one thread, two poses
@@ -645,11 +831,11 @@ def cpu_baseline(F, wl, col, hgt, total):
     for i in (0, total // 2):
         O.render(camera_path(O, hgt, m, total, i, 1, h, dst)[0], prm, col, hgt, h, w, eval_all_colors=True, nthreads=1)
     one = 2.0 / (time.perf_counter() - t1)
-    return {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "cpu_model": cpu_model(), "kind": "port",
+    return {"value": n / dt, "unit": "frames/s", "cores": threads, "cpu_model": cpu_model(), "kind": "port",
             "one_thread_value": one,
             "sample": "%d poses spread over the %d-pose path (%.1f s), C restatement of the reference (oracle/), "
-                      "OpenMP over columns, colour filter evaluated for every sample as the reference does; "
-                      "one_thread_value = 2 poses on a single thread" % (n, total, dt)}
+                      "OpenMP over columns on %d threads, colour filter evaluated for every sample as the reference does; "
+                      "one_thread_value = 2 poses on a single thread" % (n, total, dt, threads)}
 
 
 def main():
@@ -662,6 +848,7 @@ def main():
     ap.add_argument("--poses", type=int, default=0, help="override poses per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--map", type=int, default=0, help="override the map size (multiple of 256)")
+    ap.add_argument("--no-4k", action="store_true", help="skip the 4K/4000 leg that rides along with the default workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     wl = WORKLOADS[args.workload]

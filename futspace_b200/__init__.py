@@ -84,6 +84,7 @@ SYMBOLS = {
     "fsb_render_batch_device": (_ci, [_vp, _P(Camera), _ci, _P(Params), _vp, _ci, _ci, _vp]),
     "fsb_render_batch": (_ci, [_vp, _P(Camera), _ci, _P(Params), _vp, _ci, _ci, _vp]),
     "fsb_render_columns_device": (_ci, [_vp, _P(Camera), _P(Params), _vp, _ci, _ci, _ci, _ci, _vp, ctypes.c_int64]),
+    "fsb_render_columns": (_ci, [_vp, _P(Camera), _P(Params), _vp, _ci, _ci, _ci, _ci, _vp, ctypes.c_int64]),
     "fsb_effect_interpolate_device": (_ci, [_vp, _ci, _vp, _ci, _ci, _vp]),
     "fsb_effect_interpolate2_device": (_ci, [_vp, _vp, _ci, _ci, _vp]),
     "fsb_device_malloc": (_ci, [_vp, _sz, _P(_vp)]),
@@ -281,6 +282,17 @@ class Context:
     def render_columns_device(self, cam, prm, mp, h, w, col_begin, col_end, out_dev, row_stride=0):
         self._check(lib().fsb_render_columns_device(self.handle, ctypes.byref(cam), ctypes.byref(prm), mp.handle,
                                                     h, w, col_begin, col_end, out_dev, row_stride))
+
+    def render_columns(self, cam, prm, mp, h, w, col_begin, col_end, out_host, row_stride=0):
+        """fsb_render_columns: slab -> host memory at `out_host` (address of pixel (0, col_begin)), blocking."""
+        self._check(lib().fsb_render_columns(self.handle, ctypes.byref(cam), ctypes.byref(prm), mp.handle, h, w,
+                                             col_begin, col_end, out_host, row_stride))
+
+    def host_register_ptr(self, ptr, nbytes):
+        self._check(lib().fsb_host_register(self.handle, ptr, nbytes))
+
+    def host_unregister_ptr(self, ptr):
+        self._check(lib().fsb_host_unregister(self.handle, ptr))
 
     def effect_interpolate(self, frame, pd=None):
         """fut/effects.fut post-passes on a host frame: interpolate2 (pd None) or interpolate pd."""

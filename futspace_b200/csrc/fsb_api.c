@@ -528,6 +528,8 @@ static int group_size(int n, int ncols, int h) {
   return (size_t)n < g ? n : (int)g;
 }
 
+static int ensure_frame(fsb_context *ctx, int slot, size_t pixels);
+
 static int check_common(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm, const fsb_map *map,
                         int h, int w, int col_begin, int col_end, const void *out) {
   if (!ctx) return FSB_ERR_ARG;
@@ -663,7 +665,8 @@ static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_cam
   if (pl.cols) {
     /* one march warp per 32 columns: a launch group must offer enough of them to fill the device */
     const long long warps = (long long)(pl.ncols_pad / 32) * n;
-    long long min_warps = (long long)ctx->sm_count * 4;
+    /* measured crossover (round 2, profiles/r2_crossover.txt): ~60 poses at 1920 columns, ~40 at 3840 */
+    long long min_warps = (long long)ctx->sm_count * 32;
     const char *env = getenv("FSB_COLS_MIN_WARPS"); /* tuning aid */
     if (env && atoi(env) >= 0) min_warps = atoi(env);
     if (warps < min_warps) pl.cols = 0;
@@ -672,7 +675,8 @@ static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_cam
     pl.cand_cap = max_nz < h ? max_nz : h; /* one candidate per depth sample at most, and rows strictly decrease */
     if (pl.cand_cap < 1) pl.cand_cap = 1;
     /* colour pass: whole lists per warp when there are plenty of them, otherwise slices of 32 records */
-    pl.slice_len = (long long)(pl.ncols_pad / 32) * n >= (long long)ctx->sm_count * 160 ? 0 : 32;
+    const long long lists = (long long)(pl.ncols_pad / 32) * n;
+    pl.slice_len = lists >= (long long)ctx->sm_count * 160 ? 0 : lists >= (long long)ctx->sm_count * 80 ? 64 : 32;
     const char *env = getenv("FSB_COLOUR_SLICE");
     if (env && atoi(env) >= 0) pl.slice_len = atoi(env);
   }
@@ -787,6 +791,25 @@ int fsb_render_columns_device(fsb_context *ctx, const fsb_camera *cam, const fsb
   if (row_stride < col_end - col_begin) return set_err(ctx, FSB_ERR_ARG, "render: row_stride too small");
   CU(ctx, cudaSetDevice(ctx->device));
   return render_poses(ctx, cam, 1, prm, map, h, w, col_begin, col_end, out_dev, row_stride, 0);
+}
+
+/* Host-output variant of the column-split mode: the slab is rendered into the context's staging buffer and copied
+ * row by row (one 2-D DMA) into the caller's frame at its column offset.  With one process per GPU writing into one
+ * shared, page-locked host frame every GPU's PCIe link carries only its own slab. */
+int fsb_render_columns(fsb_context *ctx, const fsb_camera *cam, const fsb_params *prm, const fsb_map *map, int h, int w,
+                       int col_begin, int col_end, uint32_t *out_host, int64_t row_stride) {
+  int rc = check_common(ctx, cam, 1, prm, map, h, w, col_begin, col_end, out_host);
+  if (rc) return rc;
+  const int ncols = col_end - col_begin;
+  if (row_stride == 0) row_stride = ncols;
+  if (row_stride < ncols) return set_err(ctx, FSB_ERR_ARG, "render: row_stride too small");
+  CU(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_frame(ctx, 0, (size_t)h * ncols))) return rc;
+  if ((rc = render_poses(ctx, cam, 1, prm, map, h, w, col_begin, col_end, ctx->frame_dev[0], ncols, 0))) return rc;
+  CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)row_stride * 4, ctx->frame_dev[0], (size_t)ncols * 4, (size_t)ncols * 4,
+                            (size_t)h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return FSB_OK;
 }
 
 int fsb_render_device(fsb_context *ctx, const fsb_camera *cam, const fsb_params *prm, const fsb_map *map, int h,

@@ -259,7 +259,8 @@ __device__ __forceinline__ uint32_t colour_channel(float v00, float v01, float v
   return byte_bits(mix_unit_sqrt(wy0, sq[i1 & 255u], wy1, sq[i2 & 255u]));
 }
 
-template <bool BIL>
+/* REC4: the launch writes 4-byte records, which the host only selects when the map's alpha byte is 0x00 or 0xFF */
+template <bool BIL, bool REC4>
 __device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x, float y, const float *un, const float *sq,
                                               const float *sq_sm) {
   if (!BIL) return sample_color<MEM_TEX, false, FSB_F2I_SATURATE>(a, x, y, un, sq);
@@ -267,7 +268,7 @@ __device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x,
   const float wx1 = __fsub_rn(x, fx), wy1 = __fsub_rn(y, fy);
   const float wx0 = __fsub_rn(__fadd_rn(fx, wx1 > 0.0f ? 1.0f : 0.0f), x), wy0 = __fsub_rn(__fadd_rn(fy, wy1 > 0.0f ? 1.0f : 0.0f), y);
   const uint32_t al = a.alpha_bits;
-  if ((al == 0xFF000000u || al == 0u) && __fadd_rn(wx0, wx1) == 1.0f && __fadd_rn(wy0, wy1) == 1.0f) {
+  if ((REC4 || al == 0xFF000000u || al == 0u) && __fadd_rn(wx0, wx1) == 1.0f && __fadd_rn(wy0, wy1) == 1.0f) {
     const float u = __fmul_rn(__fadd_rn(fx, 1.0f), a.inv_r), v = __fmul_rn(__fadd_rn(fy, 1.0f), a.inv_q);
     float r00, r01, r10, r11, g00, g01, g10, g11, b00, b01, b10, b11;
     FSB_TLD4_F32C("b", a.tex_f, u, v, r10, r11, r01, r00); /* channel order of the RGBA8 texel is {B, G, R, height} */
@@ -284,7 +285,7 @@ __device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x,
 
 /* slice_len > 0: blockIdx.y selects a slice of the record index range (medium batches: more, shorter warps); the last
  * slice runs to the end of the list.  slice_len == 0: the whole list. */
-template <bool BIL>
+template <bool BIL, bool REC4>
 __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a, int slice_len) {
   __shared__ float sq_sm[256]; /* (c/255)^2: the second-stage operands of the three mixes */
   const float *un = a.lut, *sq = a.lut + 256;
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a
   uint32_t *rec4 = reinterpret_cast<uint32_t *>(a.recs) + rec0;
   uint2 *rec8 = a.recs + rec0;
   if (blockIdx.y == 0) { /* slot 0: the guard record the 8-byte walks stop at (see fsb_kernels.cu) */
-    if (a.rec4) rec4[-32] = 0u;
+    if (REC4) rec4[-32] = 0u;
     else rec8[-32] = make_uint2(0xffffffffu, 0u);
   }
   const float4 *line = reinterpret_cast<const float4 *>(a.table + (size_t)pose * a.tab_stride);
@@ -339,8 +340,8 @@ __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a
       const uint32_t row = word & FSB_ROW_MASK;
       const float x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
       const float y = __fadd_rn(l.y, __fmul_rn(fj, l.w));
-      const uint32_t colour = colour_of<BIL>(a, x, y, un, sq, sq_sm);
-      if (a.rec4) rec4[(size_t)p * 32] = (colour & 0x80FFFFFFu) | ((row & 31u) << 24);
+      const uint32_t colour = colour_of<BIL, REC4>(a, x, y, un, sq, sq_sm);
+      if (REC4) rec4[(size_t)p * 32] = (colour & 0x80FFFFFFu) | ((row & 31u) << 24);
       else rec8[(size_t)p * 32] = make_uint2(a.smooth ? word : row, colour);
       /* band index: the record that opens a new band writes its list position for that band (one predicated store in
        * the common case) and, rarely, for the bands it skipped */
@@ -397,10 +398,13 @@ extern "C" int fsb_launch_colour(const fsb_render_args *a, int slice_len, void *
   const int groups = a->ncols_pad >> 5;
   const int slices = slice_len > 0 ? (a->cand_cap + slice_len - 1) / slice_len : 1;
   dim3 grid((groups + 3) / 4, slices, a->n_poses);
-  if (a->filter == FSB_FILTER_BILINEAR)
-    fsb_colour_kernel<true><<<grid, 128, 0, s>>>(*a, slice_len);
-  else
-    fsb_colour_kernel<false><<<grid, 128, 0, s>>>(*a, slice_len);
+  if (a->filter == FSB_FILTER_BILINEAR) {
+    if (a->rec4) fsb_colour_kernel<true, true><<<grid, 128, 0, s>>>(*a, slice_len);
+    else fsb_colour_kernel<true, false><<<grid, 128, 0, s>>>(*a, slice_len);
+  } else {
+    if (a->rec4) fsb_colour_kernel<false, true><<<grid, 128, 0, s>>>(*a, slice_len);
+    else fsb_colour_kernel<false, false><<<grid, 128, 0, s>>>(*a, slice_len);
+  }
   if (launches) ++*launches;
   return (int)cudaGetLastError();
 }

@@ -31,6 +31,7 @@ class Params(ctypes.Structure):
 
 def build(force=False):
     src = [os.path.join(ORACLE_DIR, f) for f in ("fs_oracle.c", "fs_oracle.h", "Makefile")]
+    src.append(os.path.join(os.path.dirname(ORACLE_DIR), "futspace_b200", "csrc", "fsb_terrain.c"))
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return _SO
@@ -68,6 +69,8 @@ def lib():
         L.fso_interpolate.argtypes = [ci, vp, ci, ci, vp]
         L.fso_interpolate.restype = ci
         L.fso_interpolate2.argtypes = [vp, ci, ci, vp]
+        L.fsb_terrain_fbm.argtypes = [ci, ctypes.c_uint64, vp, vp]
+        L.fsb_terrain_fbm.restype = ci
         _lib = L
     return _lib
 
@@ -94,6 +97,16 @@ def get_zs(delta, dist, z0, cap=1 << 20):
     if n < 0:
         raise ValueError("invalid z-series arguments")
     return buf[:n].copy()
+
+
+def terrain_fbm(m, seed=0x5EED5EED):
+    """The benchmark terrain, from the generator source compiled into the oracle library: the CPU arm
+    of bench.py needs no product library."""
+    color = np.empty((m, m), np.uint32)
+    height = np.empty((m, m), np.int32)
+    if lib().fsb_terrain_fbm(m, seed, color.ctypes.data, height.ctypes.data):
+        raise ValueError("terrain_fbm(m=%d)" % m)
+    return color, height
 
 
 def _check_maps(color, height):

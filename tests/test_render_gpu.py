@@ -589,16 +589,23 @@ def test_column_parallel_march_on_single_frames_and_colour_slices(fsb, oracle, g
 
 
 def test_batch_paths_agree(fsb, oracle, gpu_ctx, fbm1024):
-    """A batch large enough for the column-parallel march (default path) against the lanes-over-depth march
-    (FSB_FLAG_MARCH_Z) and the oracle, frame by frame."""
+    """A batch large enough for the column-parallel march by default (80 poses x 60 groups of 32 columns) against the
+    lanes-over-depth march (FSB_FLAG_MARCH_Z) and the oracle, frame by frame; launch counts tell the two paths apart."""
     col, hgt = fbm1024
     mp = gpu_ctx.upload_map(col, hgt)
-    cams = camera_path(fsb, 1024, 96, 900)
-    a = gpu_ctx.render_batch(cams, fsb.default_params(), mp, 270, 480)
-    b = gpu_ctx.render_batch(cams, fsb.default_params(flags=fsb.FLAG_MARCH_Z), mp, 270, 480)
+    cams = camera_path(fsb, 1024, 80, 900)
+    for c in cams:
+        c.horizon = 40
+    h, w = 96, 1920
+    n0 = gpu_ctx.launch_count
+    a = gpu_ctx.render_batch(cams, fsb.default_params(), mp, h, w)
+    n1 = gpu_ctx.launch_count
+    b = gpu_ctx.render_batch(cams, fsb.default_params(flags=fsb.FLAG_MARCH_Z), mp, h, w)
+    n2 = gpu_ctx.launch_count
+    assert (n1 - n0) % 4 == 0 and (n2 - n1) % 3 == 0 and (n1 - n0) // 4 == (n2 - n1) // 3   # + the colour pass
     assert np.array_equal(a, b)
-    for i in (0, 31, 32, 63, 95):
-        want = oracle.render(ocam(oracle, cams[i]), oprm(oracle, fsb.default_params()), col, hgt & 0xFF, 270, 480)
+    for i in (0, 31, 32, 63, 79):
+        want = oracle.render(ocam(oracle, cams[i]), oprm(oracle, fsb.default_params()), col, hgt & 0xFF, h, w)
         assert np.array_equal(a[i], want), i
     mp.free()
 
@@ -621,4 +628,32 @@ def test_all_negative_terrain_integer_camera(fsb, oracle, gpu_ctx):
                 a = check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(filter=filt), 120, 160, masked=False)
                 b = gpu_ctx.render(cam, fsb.default_params(filter=filt, flags=fsb.FLAG_NO_CULL), mp, 120, 160)
                 assert np.array_equal(a, b)
+    mp.free()
+
+
+def test_config5_16384_map_column_slabs_against_the_oracle(fsb, oracle, gpu_ctx):
+    """BASELINE config 5 as stated: 7680x4320 frame, 16384^2 map, distance 4000.  Two of eight column slabs (device
+    output at their offset in the frame) and one slab through fsb_render_columns (host output) against the oracle's
+    render of the whole frame on the same map."""
+    from futspace_b200.shard import column_bounds
+    m, h, w = 16384, 4320, 7680
+    col, hgt = fsb.terrain_fbm(m)
+    mp = gpu_ctx.upload_map(col, hgt)
+    cam = fsb.Camera(m / 2 + 0.37, m / 2 + 0.73, max(160.0, float(hgt[m // 2, m // 2]) + 20.0), 2.2, 0.3 * h, 4000, 1.2, SKY)
+    prm = fsb.default_params()
+    want = oracle.render(ocam(oracle, cam), oprm(oracle, prm), col, hgt, h, w)
+    b = column_bounds(w, 8)
+    dev = gpu_ctx.device_malloc(h * w * 4)
+    for r in (0, 5):
+        gpu_ctx.render_columns_device(cam, prm, mp, h, w, b[r], b[r + 1], dev + 4 * b[r], w)
+    got = gpu_ctx.download(dev, (h, w))
+    for r in (0, 5):
+        assert np.array_equal(got[:, b[r]:b[r + 1]], want[:, b[r]:b[r + 1]]), r
+    host = np.zeros((h, w), np.uint32)
+    gpu_ctx.host_register(host)
+    gpu_ctx.render_columns(cam, prm, mp, h, w, b[3], b[4], host.ctypes.data + 4 * b[3], w)
+    gpu_ctx.host_unregister(host)
+    assert np.array_equal(host[:, b[3]:b[4]], want[:, b[3]:b[4]])
+    assert not host[:, :b[3]].any() and not host[:, b[4]:].any()      # nothing outside the slab was touched
+    gpu_ctx.device_free(dev)
     mp.free()
