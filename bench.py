@@ -379,8 +379,9 @@ def measure(torch, F, O, ctx, st, flush, wl, wl_key, m, col, hgt, mp, P, steps, 
                 e["l2_sectors_per_sample_ncu"] = r["lts_tex_read_sectors_per_pose"] / (32.0 * chunks_cull / P)
         kernels[name] = e
     # march: texture-pipe bound -- one tld4 per 32 samples, 8.2 cycles of the SM's texture pipe each
-    kernels["march"]["tex_pipe_frac"] = chunks_cull * 32 * TLD4_CYCLES_PER_SM / (SM_COUNT * f_sm * 1e3 * kern_cull["march"])
-    kernels["march"]["tex_pipe_frac_full_evaluation"] = (chunks_full * 32 * TLD4_CYCLES_PER_SM /
+    # (a counted chunk = 32 samples of one column = one warp-wide tld4's worth of lanes)
+    kernels["march"]["tex_pipe_frac"] = chunks_cull * TLD4_CYCLES_PER_SM / (SM_COUNT * f_sm * 1e3 * kern_cull["march"])
+    kernels["march"]["tex_pipe_frac_full_evaluation"] = (chunks_full * TLD4_CYCLES_PER_SM /
                                                          (SM_COUNT * f_sm * 1e3 * kern_full["march"]))
     # expand: HBM bound -- the frame must be written once
     kernels["expand"]["hbm_frac_frame_bytes_only"] = frame_alg * P / (kern_cull["expand"] * 1e-3) / 1e9 / peak

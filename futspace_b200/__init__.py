@@ -75,6 +75,7 @@ SYMBOLS = {
     "fsb_params_tests_variant": (None, [_P(Params)]),
     "fsb_get_zs": (_ci, [_cf, _cf, _cf, _vp, _ci]),
     "fsb_map_new": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _P(_vp)]),
+    "fsb_map_new_split": (_ci, [_vp, _vp, _ci, _ci, _vp, _ci, _ci, _ci, _P(_vp)]),
     "fsb_map_free": (_ci, [_vp, _vp]),
     "fsb_map_is_packed": (_ci, [_vp]),
     "fsb_map_bake_shadows": (_ci, [_vp, _vp, _P(_cf), _ci, _ci, _vp]),
@@ -93,6 +94,7 @@ SYMBOLS = {
     "fsb_host_free": (_ci, [_vp, _vp]),
     "fsb_host_register": (_ci, [_vp, _vp, _sz]),
     "fsb_host_unregister": (_ci, [_vp, _vp]),
+    "fsb_host_is_registered": (_ci, [_vp, _vp]),
     "fsb_copy_to_host": (_ci, [_vp, _vp, _vp, _sz]),
     "fsb_copy_to_device": (_ci, [_vp, _vp, _vp, _sz]),
     "fsb_ipc_export": (_ci, [_vp, _vp, _vp]),
@@ -245,6 +247,16 @@ class Context:
         self._check(lib().fsb_map_new(self.handle, color.ctypes.data, height.ctypes.data, color.shape[0],
                                       color.shape[1], 1 if mask_heights else 0, ctypes.byref(h)))
         return Map(self, h, color.shape[0], color.shape[1])
+
+    def upload_map_split(self, color, height, mask_heights=True):
+        """fsb_map_new_split: colour and height maps of different sizes (each wraps by its own size)."""
+        color = np.ascontiguousarray(color, dtype=np.uint32)
+        height = np.ascontiguousarray(height, dtype=np.int32)
+        h = _vp()
+        self._check(lib().fsb_map_new_split(self.handle, color.ctypes.data, color.shape[0], color.shape[1],
+                                            height.ctypes.data, height.shape[0], height.shape[1],
+                                            1 if mask_heights else 0, ctypes.byref(h)))
+        return Map(self, h, height.shape[0], height.shape[1])
 
     def bake_shadows(self, mp, sun, out_q=None, out_r=None):
         """fsb_map_bake_shadows -> shadowed colour map [out_q][out_r] (numpy u32)."""

@@ -66,6 +66,7 @@ struct fsb_map {
   uint32_t *packed, *color;
   int32_t *height;
   int q, r;
+  int cq, cr;                     /* colour plane size (= q, r unless fsb_map_new_split) */
   int pow2, log2r;
   uint32_t alpha_bits;
   int32_t hmax;                   /* highest (masked) terrain height */
@@ -304,6 +305,8 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   }
   m->q = q;
   m->r = r;
+  m->cq = q;
+  m->cr = r;
   m->pow2 = ((q & (q - 1)) == 0) && ((r & (r - 1)) == 0);
   while ((1 << m->log2r) < r) ++m->log2r;
   /* update_map, fut/interactive.fut:189: altitude = height & 0xFF */
@@ -402,6 +405,50 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   return FSB_OK;
 }
 
+/* Colour and height maps of different sizes, each wrapped by its own size: what `render` sees after the reference's
+ * update_map on a map that is not 1024 x 1024 (lsc.shadowed_color is baked at 1024 x 1024 whatever the input,
+ * fut/effects.fut:124-125, while lsc.altitude keeps the map's size, fut/interactive.fut:188-198).  Two-plane generic
+ * kernel only. */
+int fsb_map_new_split(fsb_context *ctx, const uint32_t *color, int cq, int cr, const int32_t *height, int q, int r,
+                      int mask_heights, fsb_map **out) {
+  if (!ctx) return FSB_ERR_ARG;
+  if (cq == q && cr == r) return fsb_map_new(ctx, color, height, q, r, mask_heights, out);
+  if (!color || !height || !out) return set_err(ctx, FSB_ERR_ARG, "fsb_map_new_split: NULL argument");
+  *out = NULL;
+  if (q <= 0 || r <= 0 || cq <= 0 || cr <= 0 || (int64_t)q * r >= (1ll << 31) || (int64_t)cq * cr >= (1ll << 31))
+    return set_err(ctx, FSB_ERR_ARG, "fsb_map_new_split: bad map size %d x %d / %d x %d", cq, cr, q, r);
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)q * r, nc = (size_t)cq * cr;
+  fsb_map *m = (fsb_map *)calloc(1, sizeof *m);
+  int32_t *hm = (int32_t *)malloc(n * 4);
+  if (!m || !hm) {
+    free(m); free(hm);
+    return set_err(ctx, FSB_ERR_NOMEM, "fsb_map_new_split: out of host memory");
+  }
+  m->q = q; m->r = r; m->cq = cq; m->cr = cr;
+  int32_t hmax = mask_heights ? (height[0] & 0xFF) : height[0];
+  for (size_t i = 0; i < n; ++i) {
+    hm[i] = mask_heights ? (height[i] & 0xFF) : height[i];
+    if (hm[i] > hmax) hmax = hm[i];
+  }
+  m->hmax = hmax;
+  m->alpha_bits = color[0] & 0xFF000000u;
+  cudaError_t e = cudaMalloc((void **)&m->color, nc * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&m->height, n * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->color, color, nc * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->height, hm, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  free(hm);
+  if (e != cudaSuccess) {
+    cudaFree(m->color); cudaFree(m->height);
+    free(m);
+    (void)cudaGetLastError();
+    return set_err(ctx, FSB_ERR_CUDA, "fsb_map_new_split: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return FSB_OK;
+}
+
 int fsb_map_free(fsb_context *ctx, fsb_map *m) {
   if (!ctx) return FSB_ERR_ARG;
   if (!m) return FSB_OK;
@@ -424,6 +471,8 @@ int fsb_map_bake_shadows(fsb_context *ctx, const fsb_map *m, const float sun[3],
                          uint32_t *out_host) {
   if (!ctx) return FSB_ERR_ARG;
   if (!m || !sun || !out_host || out_q <= 0 || out_r <= 0) return set_err(ctx, FSB_ERR_ARG, "fsb_map_bake_shadows: bad argument");
+  if (m->cq != m->q || m->cr != m->r)
+    return set_err(ctx, FSB_ERR_ARG, "fsb_map_bake_shadows: the map's colour and height planes differ in size");
   CU(ctx, cudaSetDevice(ctx->device));
   uint32_t *d = NULL;
   const size_t bytes = (size_t)out_q * out_r * 4;
@@ -705,6 +754,8 @@ static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_cam
   a.height = map->height;
   a.q = map->q;
   a.r = map->r;
+  a.cq = map->cq;
+  a.cr = map->cr;
   a.fc = sc->fc_dev;
   a.table = sc->table;
   a.tab_stride = tab_stride;
@@ -923,6 +974,16 @@ int fsb_host_register(fsb_context *ctx, void *ptr, size_t bytes) {
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
   return FSB_OK;
+}
+/* 1 when ptr lies in page-locked host memory this process registered or allocated (a DMA can target it directly) */
+int fsb_host_is_registered(fsb_context *ctx, const void *ptr) {
+  if (!ctx || !ptr) return 0;
+  struct cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return at.type == cudaMemoryTypeHost;
 }
 int fsb_host_unregister(fsb_context *ctx, void *ptr) {
   if (!ctx || !ptr) return FSB_ERR_ARG;

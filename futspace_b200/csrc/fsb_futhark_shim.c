@@ -27,6 +27,7 @@ struct futhark_context {
   size_t staging_bytes;
   uint32_t *pending_dst;
   size_t pending_bytes;
+  fsb_map *dummy;           /* init's placeholder landscape [[0],[0]] (fut/interactive.fut:38-43), created on first use */
 };
 struct futhark_u32_2d { int64_t shape[2]; uint32_t *host; uint32_t *dev; };
 struct futhark_i32_2d { int64_t shape[2]; int32_t *host; };
@@ -118,6 +119,7 @@ void futhark_context_free(struct futhark_context *ctx) {
     for (int i = 0; i < POOL_SLOTS; ++i)
       if (ctx->pool[i].dev) fsb_device_free(ctx->fsb, ctx->pool[i].dev);
     if (ctx->staging) fsb_host_free(ctx->fsb, ctx->staging);
+    if (ctx->dummy) fsb_map_free(ctx->fsb, ctx->dummy);
   }
   fsb_context_free(ctx->fsb);
   free(ctx->error);
@@ -187,6 +189,10 @@ int futhark_values_u32_2d(struct futhark_context *ctx, struct futhark_u32_2d *a,
   if (ctx->pending_dst) { /* an earlier values() not yet synced: deliver it first */
     if (fsb_context_sync(ctx->fsb)) return fail_fsb(ctx);
     flush_pending(ctx);
+  }
+  if (fsb_host_is_registered(ctx->fsb, data)) { /* page-locked destination (fsb_host_register): DMA straight into it */
+    if (fsb_copy_to_host(ctx->fsb, data, a->dev, bytes)) return fail_fsb(ctx); /* asynchronous until futhark_context_sync */
+    return 0;
   }
   if (bytes > ctx->staging_bytes) {
     if (ctx->staging) fsb_host_free(ctx->fsb, ctx->staging);
@@ -279,13 +285,9 @@ static int rebake(struct futhark_context *ctx, struct landscape *l, float sun_he
   int rc = fsb_map_bake_shadows(ctx->fsb, l->plain, sun, 1024, 1024, sh);
   fsb_map *m = NULL;
   if (!rc) {
-    if (l->q == 1024 && l->r == 1024) {
-      rc = fsb_map_new(ctx->fsb, sh, l->altitude, l->q, l->r, 0, &m);
-    } else {
-      free(sh);
-      return fail(ctx, "update_map: the reference's shadow bake is hard-wired to 1024 x 1024 maps (fut/effects.fut:124-125); "
-                       "other sizes are not supported by this shim -- use fsb_map_new / fsb_render directly");
-    }
+    /* lsc.shadowed_color is 1024 x 1024 whatever the map size; lsc.altitude keeps the map's size, and `render` wraps
+     * each by its own (fut/interactive.fut:180-181, fut/render_functions.fut:67-77,95-105) */
+    rc = fsb_map_new_split(ctx->fsb, sh, 1024, 1024, l->altitude, l->q, l->r, 0, &m);
   }
   free(sh);
   if (rc) return fail_fsb(ctx);
@@ -439,7 +441,18 @@ int futhark_entry_update_map(struct futhark_context *ctx, struct futhark_opaque_
 int futhark_entry_render(struct futhark_context *ctx, struct futhark_u32_2d **out0, const struct futhark_opaque_state *s) {
   if (!ctx || !s) return fail(ctx, "render: NULL argument");
   if (!ctx->fsb) return fail(ctx, "no device context");
-  if (!s->lsc || !s->lsc->shadowed) return fail(ctx, "render: no map loaded (call update_map first)");
+  const fsb_map *map = s->lsc ? s->lsc->shadowed : NULL;
+  if (!map) {
+    /* before the first update_map the state holds init's dummy landscape, altitude = color = shadowed_color =
+     * [[0],[0]] (fut/interactive.fut:38-43): every sample has height 0 and the empty colour 0, so the frame is the sky
+     * colour -- rendered like any other map rather than special-cased */
+    if (!ctx->dummy) {
+      const uint32_t c[2] = {0u, 0u};
+      const int32_t z[2] = {0, 0};
+      if (fsb_map_new(ctx->fsb, c, z, 2, 1, 0, &ctx->dummy)) return fail_fsb(ctx);
+    }
+    map = ctx->dummy;
+  }
   struct futhark_u32_2d *a = (struct futhark_u32_2d *)calloc(1, sizeof *a);
   if (!a) return fail(ctx, "out of memory");
   a->shape[0] = s->height; a->shape[1] = s->width;
@@ -449,7 +462,7 @@ int futhark_entry_render(struct futhark_context *ctx, struct futhark_u32_2d **ou
   fsb_params prm;
   fsb_params_default(&prm); /* #png: fut/interactive.fut:179-183 */
   if (s->smoothing_on) prm.flags |= FSB_FLAG_SMOOTHING; /* s.smoothing_mode, :182 (key `2`, :153-159) */
-  if (fsb_render_device(ctx->fsb, &s->cam, &prm, s->lsc->shadowed, s->height, s->width, a->dev, 0)) {
+  if (fsb_render_device(ctx->fsb, &s->cam, &prm, map, s->height, s->width, a->dev, 0)) {
     futhark_free_u32_2d(ctx, a);
     return fail_fsb(ctx);
   }

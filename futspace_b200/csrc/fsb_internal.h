@@ -38,7 +38,8 @@ typedef struct fsb_render_args {
   float inv_r, inv_q;       /* 1/r, 1/q for normalised texture coordinates */
   const uint32_t *color;    /* [q][r] argb  */
   const int32_t *height;    /* [q][r]       */
-  int32_t q, r;
+  int32_t q, r;             /* height plane (and every packed form): rows, columns */
+  int32_t cq, cr;           /* colour plane of the generic path (= q, r unless fsb_map_new_split) */
   const fsb_frame_consts *fc; /* device, [n_poses] */
   const float *table;       /* device, [n_poses][tab_stride]: per pose kcap x {sx,sy,dx,dy}, then kcap x inv_z    */
   int32_t tab_stride;       /* floats per pose = 5 * kcap, kcap = 32 * (n_chunks + 6): the march prefetches past the last chunk */

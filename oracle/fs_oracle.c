@@ -257,9 +257,9 @@ static inline uint32_t smooth_pixel(uint32_t c, uint32_t cprev, int32_t y, int32
 
 /* Smoothing #on, sequential statement (see fs_oracle.h): per column the list of samples that lower the y-buffer,
  * then rows top-down. */
-static int render_smooth(const fso_camera *cam, const fso_params *prm, const uint32_t *color, const int32_t *height,
-                         int q, int r, int h, int w, uint32_t *out, int eval_all, int nthreads, const depth_line *L,
-                         int n) {
+static int render_smooth(const fso_camera *cam, const fso_params *prm, const uint32_t *color, int cq, int cr,
+                         const int32_t *height, int q, int r, int h, int w, uint32_t *out, int eval_all, int nthreads,
+                         const depth_line *L, int n) {
   const int bil = prm->filter == FSO_FILTER_BILINEAR, m = prm->f2i_mode;
 #ifdef _OPENMP
   if (nthreads <= 0) nthreads = omp_get_max_threads();
@@ -280,10 +280,10 @@ static int render_smooth(const fso_camera *cam, const fso_params *prm, const uin
         seg_point(&L[k], j, &x, &y);
         float hgt = bil ? fso_height_bilinear(height, q, r, x, y, m) : fso_height_nearest(height, q, r, x, y, m);
         uint32_t c = 0;
-        if (eval_all) c = bil ? fso_color_bilinear(color, q, r, x, y, m) : fso_color_nearest(color, q, r, x, y, m);
+        if (eval_all) c = bil ? fso_color_bilinear(color, cq, cr, x, y, m) : fso_color_nearest(color, cq, cr, x, y, m);
         int32_t yy = project(cam, prm, &L[k], hgt);
         if (yy < ybuf) { /* occlude2 :87-90 keeps the earlier sample on ties */
-          if (!eval_all) c = bil ? fso_color_bilinear(color, q, r, x, y, m) : fso_color_nearest(color, q, r, x, y, m);
+          if (!eval_all) c = bil ? fso_color_bilinear(color, cq, cr, x, y, m) : fso_color_nearest(color, cq, cr, x, y, m);
           rk[cnt] = k; ry[cnt] = yy; rcol[cnt] = c;
           ++cnt;
           ybuf = yy;
@@ -313,8 +313,14 @@ static int render_smooth(const fso_camera *cam, const fso_params *prm, const uin
 
 int fso_render(const fso_camera *cam, const fso_params *prm, const uint32_t *color, const int32_t *height,
                int q, int r, int h, int w, uint32_t *out, int eval_all, int nthreads) {
+  return fso_render_split(cam, prm, color, q, r, height, q, r, h, w, out, eval_all, nthreads);
+}
+
+int fso_render_split(const fso_camera *cam, const fso_params *prm, const uint32_t *color, int cq, int cr,
+                     const int32_t *height, int q, int r, int h, int w, uint32_t *out, int eval_all, int nthreads) {
   int rc = check_args(cam, prm, color, height, q, r, h, w, out);
   if (rc) return rc;
+  if (cq <= 0 || cr <= 0) return 2;
   int n = 0;
   depth_line *L = make_lines(cam, prm, w, &n);
   if (!L) return 3;
@@ -326,7 +332,7 @@ int fso_render(const fso_camera *cam, const fso_params *prm, const uint32_t *col
   (void)nthreads;
 #endif
   if (prm->smoothing) {
-    rc = render_smooth(cam, prm, color, height, q, r, h, w, out, eval_all, nthreads, L, n);
+    rc = render_smooth(cam, prm, color, cq, cr, height, q, r, h, w, out, eval_all, nthreads, L, n);
     free(L);
     return rc;
   }
@@ -342,10 +348,10 @@ int fso_render(const fso_camera *cam, const fso_params *prm, const uint32_t *col
         seg_point(&L[k], j, &x, &y);
         float hgt = bil ? fso_height_bilinear(height, q, r, x, y, m) : fso_height_nearest(height, q, r, x, y, m);
         uint32_t c = 0;
-        if (eval_all) c = bil ? fso_color_bilinear(color, q, r, x, y, m) : fso_color_nearest(color, q, r, x, y, m);
+        if (eval_all) c = bil ? fso_color_bilinear(color, cq, cr, x, y, m) : fso_color_nearest(color, cq, cr, x, y, m);
         int32_t yy = project(cam, prm, &L[k], hgt);
         if (yy < ybuf) {
-          if (!eval_all) c = bil ? fso_color_bilinear(color, q, r, x, y, m) : fso_color_nearest(color, q, r, x, y, m);
+          if (!eval_all) c = bil ? fso_color_bilinear(color, cq, cr, x, y, m) : fso_color_nearest(color, cq, cr, x, y, m);
           col[yy] = c;
           ybuf = yy;
         }

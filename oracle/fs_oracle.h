@@ -78,6 +78,12 @@ int fso_render(const fso_camera *cam, const fso_params *prm, const uint32_t *col
                const int32_t *height, int q, int r, int h, int w, uint32_t *out,
                int eval_all_colors, int nthreads);
 
+/* The same with a colour map whose size differs from the height map's; each sampler wraps by the size of the array it
+ * reads (fut/render_functions.fut:63-105 take the array's own shape).  This is the state update_map leaves for maps that
+ * are not 1024 x 1024: shadowed_color is always baked at 1024 x 1024 (fut/effects.fut:124-125, fut/interactive.fut:194-198). */
+int fso_render_split(const fso_camera *cam, const fso_params *prm, const uint32_t *color, int cq, int cr,
+                     const int32_t *height, int q, int r, int h, int w, uint32_t *out, int eval_all, int nthreads);
+
 /* The reference's pipeline taken literally: materialise [n_z][w] (colour, y) pairs
  * (voxel_renderer.fut:215-228), per column inclusive scan with `occlude` and neutral (0,h)
  * (:231), scatter into replicate h 0 (:244), inclusive scan with `fill_vline` (:246), sky map

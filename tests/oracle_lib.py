@@ -61,6 +61,8 @@ def lib():
             f.restype = rt
         L.fso_render.argtypes = [P(Camera), P(Params), vp, vp, ci, ci, ci, ci, vp, ci, ci]
         L.fso_render.restype = ci
+        L.fso_render_split.argtypes = [P(Camera), P(Params), vp, ci, ci, vp, ci, ci, ci, ci, vp, ci, ci]
+        L.fso_render_split.restype = ci
         L.fso_render_literal.argtypes = [P(Camera), P(Params), vp, vp, ci, ci, ci, ci, vp]
         L.fso_render_literal.restype = ci
         L.fso_mask_heights.argtypes = [vp, ctypes.c_long]
@@ -124,6 +126,18 @@ def render(cam, prm, color, height, h, w, eval_all_colors=False, nthreads=0):
                           1 if eval_all_colors else 0, nthreads)
     if rc:
         raise RuntimeError("fso_render failed rc=%d" % rc)
+    return out
+
+
+def render_split(cam, prm, color, height, h, w, nthreads=0):
+    """Colour and height maps of different sizes (the state update_map leaves for maps that are not 1024 x 1024)."""
+    color = np.ascontiguousarray(color, dtype=np.uint32)
+    height = np.ascontiguousarray(height, dtype=np.int32)
+    out = np.empty((h, w), np.uint32)
+    rc = lib().fso_render_split(ctypes.byref(cam), ctypes.byref(prm), color.ctypes.data, color.shape[0], color.shape[1],
+                                height.ctypes.data, height.shape[0], height.shape[1], h, w, out.ctypes.data, 0, nthreads)
+    if rc:
+        raise RuntimeError("fso_render_split failed rc=%d" % rc)
     return out
 
 

@@ -2,6 +2,8 @@
 and the full c/interactive.c call sequence on the GPU against the oracle."""
 import math
 
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -123,4 +125,78 @@ def test_interactive_c_call_sequence_matches_oracle(fsb, oracle, c1w_d1):
     want = oracle.render(cam, oracle.default_params(smoothing=1), shadowed, hgt, 384, 512)
     assert np.array_equal(frame, want)
     assert not np.array_equal(frame, oracle.render(cam, oracle.default_params(), shadowed, hgt, 384, 512))
+    s.close()
+
+
+@pytest.mark.gpu
+def test_render_before_update_map_draws_the_dummy_landscape(fsb, oracle):
+    """init's placeholder landscape is altitude = color = shadowed_color = [[0],[0]] (fut/interactive.fut:38-43): every
+    sample has height 0 and the empty colour, so `render` returns the sky colour everywhere -- 0 before the first step,
+    argb.scale 0xFF9090e0 sun_height after it (:163)."""
+    s = FS.Session()
+    s.init()
+    s.resize(96, 128)
+    frame = s.render()
+    assert frame.shape == (96, 128) and (frame == 0).all()
+    s.step()
+    frame = s.render()
+    sky = oracle.lib().fso_scale(0xFF9090E0, 0.1)
+    assert (frame == sky).all()
+    x, y, angle, height, horizon, distance, _, _, fov = s.text_content()
+    want = oracle.render(oracle.Camera(x, y, height, angle, horizon, distance, fov, sky), oracle.default_params(),
+                         np.zeros((2, 1), np.uint32), np.zeros((2, 1), np.int32), 96, 128)
+    assert np.array_equal(frame, want)
+    s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(300, 517), (2048, 1024)])
+def test_update_map_of_a_map_that_is_not_1024_square(fsb, oracle, fbm1024, shape):
+    """update_map bakes lsc.shadowed_color at 1024 x 1024 whatever the map size (fut/effects.fut:124-125) and keeps
+    lsc.altitude at the map's size (fut/interactive.fut:188-198); `render` then wraps each by its own size."""
+    col, hgt = fbm1024
+    q, r = shape
+    cmap = np.ascontiguousarray(np.tile(col, (2, 1))[:q, :r])
+    hmap = np.ascontiguousarray(np.tile(hgt, (2, 1))[:q, :r])
+    s = FS.Session()
+    s.init()
+    s.update_map(cmap, hmap)
+    s.resize(240, 320)
+    s.step()
+    frame = s.render()
+    sun = oracle.sun_vector(0.1, 0.1)
+    shadowed = oracle.bake_shadows(cmap, hmap, sun, 1024, 1024)
+    sky = oracle.lib().fso_scale(0xFF9090E0, 0.1)
+    x, y, angle, height, horizon, distance, _, _, fov = s.text_content()
+    cam = oracle.Camera(x, y, height, angle, horizon, distance, fov, sky)
+    want = oracle.render_split(cam, oracle.default_params(), shadowed, hmap, 240, 320)
+    assert np.array_equal(frame, want)
+    assert len(np.unique(frame)) > 20
+    s.close()
+
+
+@pytest.mark.gpu
+def test_values_into_a_registered_buffer_needs_no_staging_copy(fsb, oracle, c1w_d1):
+    """futhark_values_u32_2d into a page-locked destination (fsb_host_register on the host's frame buffer) is a
+    single DMA; into pageable memory it goes through the shim's pinned staging buffer.  Same pixels either way."""
+    rgb, hgt = c1w_d1
+    s = FS.Session()
+    s.init()
+    s.update_map(rgb | 0xFF000000, hgt)
+    s.resize(200, 256)
+    s.step()
+    plain = s.render()
+    L = s.L
+    out = FS.vp()
+    assert L.futhark_entry_render(s.ctx, ctypes.byref(out), s.state) == 0
+    buf = np.zeros((200, 256), np.uint32)
+    raw = ctypes.c_void_p.from_address(s.ctx)   # struct futhark_context { fsb_context *fsb; ... }
+    F = fsb.lib()
+    assert F.fsb_host_register(raw, buf.ctypes.data, buf.nbytes) == 0
+    assert F.fsb_host_is_registered(raw, buf.ctypes.data) == 1 and F.fsb_host_is_registered(raw, plain.ctypes.data) == 0
+    assert L.futhark_values_u32_2d(s.ctx, out, buf.ctypes.data) == 0
+    assert L.futhark_context_sync(s.ctx) == 0
+    assert F.fsb_host_unregister(raw, buf.ctypes.data) == 0
+    L.futhark_free_u32_2d(s.ctx, out)
+    assert np.array_equal(buf, plain)
     s.close()
