@@ -182,7 +182,7 @@ int fsb_context_new(int device, fsb_context **out) {
   if (device < 0 || device >= count) return FSB_ERR_ARG;
   struct cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FSB_ERR_CUDA;
-  if (prop.major != 10) return FSB_ERR_NO_DEVICE; /* kernels are built for sm_100a only */
+  if (prop.major != 10 || prop.minor != 0) return FSB_ERR_NO_DEVICE; /* the library ships sm_100a SASS only (no PTX): not even sm_103 can run it */
   fsb_context *ctx = (fsb_context *)calloc(1, sizeof *ctx);
   if (!ctx) return FSB_ERR_NOMEM;
   ctx->device = device;
@@ -342,7 +342,11 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   cudaError_t e = cudaMalloc((void **)&m->color, n * 4);
   if (e == cudaSuccess) e = cudaMalloc((void **)&m->height, n * 4);
   if (e == cudaSuccess && packable && tileable) e = cudaMalloc((void **)&m->packed, n * 4);
-  if (e == cudaSuccess && packable && q <= 65536 && r <= 131072) {
+  struct cudaDeviceProp prop;
+  int gather_ok = cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && r <= prop.maxTexture2DGather[0] &&
+                  q <= prop.maxTexture2DGather[1];
+  cudaError_t e_planes = e;
+  if (e == cudaSuccess && packable && gather_ok) {
     struct cudaChannelFormatDesc cd = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
     e = cudaMallocArray(&m->array, &cd, (size_t)r, (size_t)q, cudaArrayTextureGather);
     if (e == cudaSuccess)
@@ -381,6 +385,19 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
         }
       }
       free(hh);
+    }
+    if (e != cudaSuccess) { /* no texture path for this map (size limits, array memory): the tiled / two-plane kernels need none */
+      (void)cudaGetLastError();
+      cudaStreamSynchronize(ctx->stream);
+      if (m->tex) cudaDestroyTextureObject(m->tex);
+      if (m->tex_h) cudaDestroyTextureObject(m->tex_h);
+      if (m->tex_f) cudaDestroyTextureObject(m->tex_f);
+      if (m->array) cudaFreeArray(m->array);
+      if (m->array_h) cudaFreeArray(m->array_h);
+      m->tex = m->tex_h = m->tex_f = 0;
+      m->array = m->array_h = NULL;
+      (void)cudaGetLastError();
+      e = e_planes;
     }
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->color, color, n * 4, cudaMemcpyHostToDevice, ctx->stream);
@@ -917,6 +934,10 @@ int fsb_render_batch(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_
   int rc = check_common(ctx, cams, n, prm, map, h, w, 0, w, out_host);
   if (rc) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
+  for (int i = 0; i < n; ++i) /* every pose is validated before anything is queued: no DMA into out_host is pending on an error return */
+    if (zs_length(prm->delta, cams[i].distance, prm->z0) < 0)
+      return set_err(ctx, FSB_ERR_RANGE, "render: z-series undefined for pose %d (distance=%g delta=%g z0=%g)", i,
+                     (double)cams[i].distance, (double)prm->delta, (double)prm->z0);
   const size_t frame = (size_t)h * w;
   size_t chunk = (64u << 20) / (frame * 4);
   if (chunk < 1) chunk = 1;
@@ -930,7 +951,11 @@ int fsb_render_batch(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_
     const int s = it & 1;
     const int c = (int)((size_t)n - i < chunk ? (size_t)n - i : chunk);
     if (it >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copied[s], 0));
-    if ((rc = render_poses(ctx, cams + i, c, prm, map, h, w, 0, w, ctx->frame_dev[s], w, (int64_t)frame))) return rc;
+    if ((rc = render_poses(ctx, cams + i, c, prm, map, h, w, 0, w, ctx->frame_dev[s], w, (int64_t)frame))) {
+      cudaStreamSynchronize(ctx->stream); /* earlier chunks may still be on their way into out_host */
+      cudaStreamSynchronize(ctx->copy_stream);
+      return rc;
+    }
     CU(ctx, cudaEventRecord(ctx->rendered[s], ctx->stream));
     CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->rendered[s], 0));
     CU(ctx, cudaMemcpyAsync(out_host + i * frame, ctx->frame_dev[s], (size_t)c * frame * 4, cudaMemcpyDeviceToHost,

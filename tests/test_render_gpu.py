@@ -175,6 +175,14 @@ def test_error_behaviour(fsb, gpu_ctx, fbm1024):
     assert e.value.code == fsb.ERR_RANGE
     # the context stays usable after an error
     gpu_ctx.render(cam, fsb.default_params(), mp, 64, 64)
+    # a bad pose late in a host batch is reported before anything is queued: the output buffer is left untouched
+    cams = [fsb.Camera(1, 2, 100, 0, 50, 100.0, 1.2, SKY) for _ in range(40)]
+    cams[37].distance = -5.0
+    out = np.full((40, 1024, 1024), 0xDEADBEEF, np.uint32)      # 4 MiB frames: the batch would span three staging chunks
+    with pytest.raises(fsb.FsbError) as e:
+        gpu_ctx.render_batch(cams, fsb.default_params(), mp, 1024, 1024, out=out)
+    assert e.value.code == fsb.ERR_RANGE and "pose 37" in str(e.value)
+    assert (out == 0xDEADBEEF).all()
     mp.free()
 
 
@@ -585,6 +593,21 @@ def test_column_parallel_march_on_single_frames_and_colour_slices(fsb, oracle, g
     # tests variant (z0 = 1, sky sentinel, nearest), a tall narrow frame, and the tallest frame the library takes
     check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(512, 800, 78, 0, 100, 800, 1, SKY), fsb.tests_variant_params(), 400, 33)
     check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(512.37, 512.73, 150, 2.2, 9000, 700, 1.2, SKY), fsb.default_params(), 32768, 40)
+    mp.free()
+
+
+@pytest.mark.parametrize("flags", [8, 8 | 16], ids=["default", "march_z"])
+def test_smoothing_at_the_maximum_frame_height(fsb, oracle, gpu_ctx, fbm1024, monkeypatch, flags):
+    """h = 32768 = 2^15: the neutral element (0, h, 0) of the smoothing scan does not fit the 15 row bits of a record;
+    the first visible sample (k = 1 against the neutral k = 0) must still be blended exactly as the oracle does."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    for cols in ("0", None):
+        if cols is not None:
+            monkeypatch.setenv("FSB_COLS_MIN_WARPS", cols)
+        for horizon in (9000, 31000):
+            cam = fsb.Camera(512.37, 512.73, 150, 2.2, horizon, 700, 1.2, SKY)
+            check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, fsb.default_params(flags=flags), 32768, 8)
     mp.free()
 
 
