@@ -174,6 +174,14 @@ static int make_consts(const fsb_camera *cam, const fsb_params *prm, const fsb_m
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* the expand stream of the overlap mode gets the highest priority: its CTAs are dispatched ahead of the march's whenever
+ * an SM has room, so the frame stores interleave with the next group's march instead of queueing behind it */
+static cudaError_t create_expand_stream(cudaStream_t *s) {
+  int lo = 0, hi = 0;
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi);
+}
+
 int fsb_context_new(int device, fsb_context **out) {
   if (!out) return FSB_ERR_ARG;
   *out = NULL;
@@ -194,7 +202,7 @@ int fsb_context_new(int device, fsb_context **out) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->expand_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      create_expand_stream(&ctx->expand_stream) != cudaSuccess) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->expand_stream) cudaStreamDestroy(ctx->expand_stream);

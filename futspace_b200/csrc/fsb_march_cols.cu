@@ -112,6 +112,24 @@ __device__ __forceinline__ size_t cand_group_base(const fsb_render_args &a, int 
   return ((size_t)pose * (a.ncols_pad >> 5) + group) * a.cand_cap * 32;
 }
 
+/* U consecutive inv_z of the staged chunk with the widest shared-memory loads (p is U * 4-byte aligned) */
+template <int U>
+__device__ __forceinline__ void load_inv_z(const float *p, float (&iz)[U]) {
+  if (U % 4 == 0) {
+#pragma unroll
+    for (int v = 0; v < U / 4; ++v) {
+      const float4 t = reinterpret_cast<const float4 *>(p)[v];
+      iz[4 * v] = t.x; iz[4 * v + 1] = t.y; iz[4 * v + 2] = t.z; iz[4 * v + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < U / 2; ++v) {
+      const float2 t = reinterpret_cast<const float2 *>(p)[v];
+      iz[2 * v] = t.x; iz[2 * v + 1] = t.y;
+    }
+  }
+}
+
 /* U = depth steps per register set; two sets are in flight (the gathers of one are issued before the other is resolved).
  *
  * Depth table: the 640 bytes of a chunk of 32 steps ({sx,sy,dx,dy} x 32, inv_z x 32) are the same for every column, so
@@ -204,16 +222,19 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
         for (int i = 0; i < 32; i += 2 * U) {
 #pragma unroll
           for (int u = 0; u < U; ++u) cstep_issue<BIL>(sb[u], a, tl[i + U + u], fj);
+          float iza[U], izb[U];
+          load_inv_z<U>(tz + i, iza);
+          load_inv_z<U>(tz + i + U, izb);
 #pragma unroll
           for (int u = 0; u < U; ++u)
-            cstep_resolve<BIL>(sa[u], tz[i + u], cam_h, horizon, kw + ((uint32_t)(i + u) << FSB_ROW_BITS), st);
+            cstep_resolve<BIL>(sa[u], iza[u], cam_h, horizon, kw + ((uint32_t)(i + u) << FSB_ROW_BITS), st);
           /* next set: the following steps of this chunk, or the head of the next one (a repeated last sample in the
            * padding projects to the same row and `occlude` keeps the earlier one) */
 #pragma unroll
           for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, i + 2 * U < 32 ? tl[i + 2 * U + u] : tl_next[u], fj);
 #pragma unroll
           for (int u = 0; u < U; ++u)
-            cstep_resolve<BIL>(sb[u], tz[i + U + u], cam_h, horizon, kw + ((uint32_t)(i + U + u) << FSB_ROW_BITS), st);
+            cstep_resolve<BIL>(sb[u], izb[u], cam_h, horizon, kw + ((uint32_t)(i + U + u) << FSB_ROW_BITS), st);
         }
       }
       cp_async_wait_all();
@@ -251,18 +272,25 @@ __device__ __forceinline__ uint32_t byte_bits(float v) { /* 0x4B0000nn with nn =
 __device__ __forceinline__ float mix_unit_sqrt(float m1, float s1, float m2, float s2) {
   return sqrt_rn_unit(__fadd_rn(__fmul_rn(m1, s1), __fmul_rn(m2, s2)));
 }
+/* (nn/255)^2 from the shared-memory table for bits = 0x4B0000nn: the address is one multiply-add,
+ * bits * 4 + (table - 0x4B000000 * 4) in wrap-around 32-bit arithmetic, instead of a mask and a shift */
+__device__ __forceinline__ float sq_of_bits(uint32_t bits, uint32_t sq_sm_biased) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(bits * 4u + sq_sm_biased));
+  return v;
+}
 /* one channel of png_color_filtered from the four normalised texels: -> 0x4B0000nn */
 __device__ __forceinline__ uint32_t colour_channel(float v00, float v01, float v10, float v11, float wx0, float wx1, float wy0,
-                                                   float wy1, const float *__restrict__ sq) {
+                                                   float wy1, uint32_t sq_sm_biased) {
   const uint32_t i1 = byte_bits(mix_unit_sqrt(wx0, __fmul_rn(v00, v00), wx1, __fmul_rn(v01, v01)));
   const uint32_t i2 = byte_bits(mix_unit_sqrt(wx0, __fmul_rn(v10, v10), wx1, __fmul_rn(v11, v11)));
-  return byte_bits(mix_unit_sqrt(wy0, sq[i1 & 255u], wy1, sq[i2 & 255u]));
+  return byte_bits(mix_unit_sqrt(wy0, sq_of_bits(i1, sq_sm_biased), wy1, sq_of_bits(i2, sq_sm_biased)));
 }
 
 /* REC4: the launch writes 4-byte records, which the host only selects when the map's alpha byte is 0x00 or 0xFF */
 template <bool BIL, bool REC4>
 __device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x, float y, const float *un, const float *sq,
-                                              const float *sq_sm) {
+                                              uint32_t sq_sm) {
   if (!BIL) return sample_color<MEM_TEX, false, FSB_F2I_SATURATE>(a, x, y, un, sq);
   const float fx = floorf(x), fy = floorf(y);
   const float wx1 = __fsub_rn(x, fx), wy1 = __fsub_rn(y, fy);
@@ -289,9 +317,14 @@ template <bool BIL, bool REC4>
 __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a, int slice_len) {
   __shared__ float sq_sm[256]; /* (c/255)^2: the second-stage operands of the three mixes */
   const float *un = a.lut, *sq = a.lut + 256;
+  __shared__ uint32_t bias_slot;
   sq_sm[threadIdx.x] = sq[threadIdx.x];
   sq_sm[threadIdx.x + 128] = sq[threadIdx.x + 128];
+  /* table address minus 0x4B000000 * 4 (see sq_of_bits), passed through shared memory so that ptxas keeps it in one
+   * register instead of re-deriving the difference at each of the six look-ups of a record */
+  if (threadIdx.x == 0) bias_slot = (uint32_t)__cvta_generic_to_shared(sq_sm) - 0x4B000000u * 4u;
   __syncthreads();
+  const uint32_t sq_sm_biased = *reinterpret_cast<volatile uint32_t *>(&bias_slot);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pose = blockIdx.z;
   const int ncols = a.col_end - a.col_begin;
@@ -340,7 +373,7 @@ __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a
       const uint32_t row = word & FSB_ROW_MASK;
       const float x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
       const float y = __fadd_rn(l.y, __fmul_rn(fj, l.w));
-      const uint32_t colour = colour_of<BIL, REC4>(a, x, y, un, sq, sq_sm);
+      const uint32_t colour = colour_of<BIL, REC4>(a, x, y, un, sq, sq_sm_biased);
       if (REC4) rec4[(size_t)p * 32] = (colour & 0x80FFFFFFu) | ((row & 31u) << 24);
       else rec8[(size_t)p * 32] = make_uint2(a.smooth ? word : row, colour);
       /* band index: the record that opens a new band writes its list position for that band (one predicated store in
