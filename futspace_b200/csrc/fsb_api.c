@@ -20,14 +20,11 @@
 #define FSB_MAX_NZ (1 << 22)
 #define FSB_MAX_POSES_PER_LAUNCH 32768
 
-/* Per-launch-group device scratch.  A context owns two sets so that the expand kernel of one launch group (DRAM-bound,
- * on its own stream) can overlap the march of the next (issue-bound); everything else uses set 0 only. */
+/* Per-launch-group device scratch. */
 typedef struct fsb_scratch {
   fsb_frame_consts *fc_dev, *fc_host;
   int fc_cap;
   cudaEvent_t fc_free;            /* pinned pose-constant staging may be rewritten */
-  cudaEvent_t coloured, expanded; /* overlap mode: records complete / scratch set free again */
-  int busy;                       /* an expand of this set is in flight on the expand stream */
   float *table;                   /* per-pose depth tables (blocked by chunk, fsb_kernels.cu) */
   size_t tab_cap;                 /* floats */
   void *recs;                     /* march -> expand record lists */
@@ -39,8 +36,8 @@ typedef struct fsb_scratch {
 
 struct fsb_context {
   int device;
-  cudaStream_t stream, copy_stream, expand_stream;
-  fsb_scratch sc[2];
+  cudaStream_t stream, copy_stream;
+  fsb_scratch sc;
   cudaEvent_t rendered[2], copied[2];
   char err[512];
   int64_t launches;
@@ -54,7 +51,6 @@ struct fsb_context {
   int prof_pending;
   unsigned long long *stats_dev;  /* profiling counters: chunks evaluated, records emitted */
   int force_rec8;                 /* env FSB_REC8: always 8-byte records */
-  int overlap_poses;              /* env FSB_OVERLAP: poses per launch group when expand overlaps the next march (0: off) */
   const float *lut;               /* device address of the colour look-up table */
   int force_march_z;              /* env FSB_MARCH_Z: always the lanes-over-depth march */
   char name[128];
@@ -174,14 +170,6 @@ static int make_consts(const fsb_camera *cam, const fsb_params *prm, const fsb_m
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* the expand stream of the overlap mode gets the highest priority: its CTAs are dispatched ahead of the march's whenever
- * an SM has room, so the frame stores interleave with the next group's march instead of queueing behind it */
-static cudaError_t create_expand_stream(cudaStream_t *s) {
-  int lo = 0, hi = 0;
-  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
-  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi);
-}
-
 int fsb_context_new(int device, fsb_context **out) {
   if (!out) return FSB_ERR_ARG;
   *out = NULL;
@@ -201,11 +189,9 @@ int fsb_context_new(int device, fsb_context **out) {
   snprintf(ctx->name, sizeof ctx->name, "%.127s", prop.name);
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      create_expand_stream(&ctx->expand_stream) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->expand_stream) cudaStreamDestroy(ctx->expand_stream);
     free(ctx);
     return FSB_ERR_CUDA;
   }
@@ -214,21 +200,14 @@ int fsb_context_new(int device, fsb_context **out) {
   if (fsb_launch_lut_init(ctx->stream) != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
-    cudaStreamDestroy(ctx->expand_stream);
     free(ctx);
     return FSB_ERR_CUDA;
   }
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&ctx->rendered[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->copied[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->sc[i].fc_free, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->sc[i].coloured, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->sc[i].expanded, cudaEventDisableTiming);
   }
-  {
-    const char *e = getenv("FSB_OVERLAP");
-    ctx->overlap_poses = e ? atoi(e) : 0;
-  }
+  cudaEventCreateWithFlags(&ctx->sc.fc_free, cudaEventDisableTiming);
   ctx->lut = fsb_lut_device_address();
   *out = ctx;
   return FSB_OK;
@@ -239,9 +218,8 @@ void fsb_context_free(fsb_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
-  cudaStreamSynchronize(ctx->expand_stream);
-  for (int i = 0; i < 2; ++i) {
-    fsb_scratch *sc = &ctx->sc[i];
+  {
+    fsb_scratch *sc = &ctx->sc;
     cudaFree(sc->fc_dev);
     cudaFreeHost(sc->fc_host);
     cudaFree(sc->table);
@@ -250,8 +228,6 @@ void fsb_context_free(fsb_context *ctx) {
     cudaFree(sc->cand);
     cudaFree(sc->cand_cnt);
     cudaEventDestroy(sc->fc_free);
-    cudaEventDestroy(sc->coloured);
-    cudaEventDestroy(sc->expanded);
   }
   cudaFree(ctx->frame_dev[0]);
   cudaFree(ctx->frame_dev[1]);
@@ -264,7 +240,6 @@ void fsb_context_free(fsb_context *ctx) {
   }
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
-  cudaStreamDestroy(ctx->expand_stream);
   free(ctx);
 }
 
@@ -274,7 +249,6 @@ int fsb_context_sync(fsb_context *ctx) {
   if (!ctx) return FSB_ERR_ARG;
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
-  CU(ctx, cudaStreamSynchronize(ctx->expand_stream));
   return FSB_OK;
 }
 
@@ -529,7 +503,6 @@ int fsb_map_is_packed(const fsb_map *m) { return m && (m->packed != NULL || m->t
 static int ensure_tables(fsb_context *ctx, fsb_scratch *sc, int n_poses, int tab_stride) {
   if (n_poses > sc->fc_cap) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->expand_stream));
     cudaFree(sc->fc_dev);
     cudaFreeHost(sc->fc_host);
     sc->fc_dev = NULL; sc->fc_host = NULL; sc->fc_cap = 0;
@@ -556,7 +529,6 @@ static int ensure_tables(fsb_context *ctx, fsb_scratch *sc, int n_poses, int tab
 static int grow(fsb_context *ctx, void **ptr, size_t *cap, size_t need) {
   if (need <= *cap) return FSB_OK;
   CU(ctx, cudaStreamSynchronize(ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->expand_stream));
   cudaFree(*ptr);
   *ptr = NULL;
   *cap = 0;
@@ -670,13 +642,11 @@ int fsb_context_get_profile(fsb_context *ctx, double *ms, int64_t *launches) {
   return FSB_OK;
 }
 
-/* Queue set-up + render kernels for n poses (n <= FSB_MAX_POSES_PER_LAUNCH) on ctx->stream, using scratch set `set`.
- * overlap != 0: the expand kernel goes to ctx->expand_stream (ordered after the colour pass by an event) so that the
- * caller can queue the next group's march behind this group's colour pass; the caller joins the streams at the end. */
-static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_camera *cams, int n, const fsb_params *prm,
-                           const fsb_map *map, int h, int w, int col_begin, int col_end, uint32_t *out_dev,
-                           int64_t row_stride, int64_t pose_stride) {
-  fsb_scratch *sc = &ctx->sc[set];
+/* Queue set-up + render kernels for n poses (n <= FSB_MAX_POSES_PER_LAUNCH) on ctx->stream. */
+static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm, const fsb_map *map,
+                        int h, int w, int col_begin, int col_end, uint32_t *out_dev, int64_t row_stride,
+                        int64_t pose_stride) {
+  fsb_scratch *sc = &ctx->sc;
   fsb_frame_consts single;
   int max_nz = 0;
   if (row_stride > (int64_t)(INT32_MAX / 4)) /* fsb_expand_kernel forms row offsets from a 32-bit byte stride */
@@ -755,10 +725,6 @@ static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_cam
     if (env && atoi(env) >= 0) pl.slice_len = atoi(env);
   }
   if ((rc = ensure_scratch(ctx, sc, n, ncols, h, &pl))) return rc;
-  if (sc->busy) { /* an earlier group's expand still reads this scratch set (and its pose constants) */
-    CU(ctx, cudaStreamWaitEvent(ctx->stream, sc->expanded, 0));
-    sc->busy = 0;
-  }
   if (n > 1) {
     CU(ctx, cudaMemcpyAsync(sc->fc_dev, sc->fc_host, sizeof(fsb_frame_consts) * (size_t)n, cudaMemcpyHostToDevice,
                             ctx->stream));
@@ -827,35 +793,11 @@ static int render_poses_on(fsb_context *ctx, int set, int overlap, const fsb_cam
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
   }
   if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[3], ctx->stream));
-  if (overlap) {
-    CU(ctx, cudaEventRecord(sc->coloured, ctx->stream));
-    CU(ctx, cudaStreamWaitEvent(ctx->expand_stream, sc->coloured, 0));
-    CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->expand_stream, &ctx->launches));
-    CU(ctx, cudaEventRecord(sc->expanded, ctx->expand_stream));
-    sc->busy = 1;
-  } else {
-    CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));
-  }
+  CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));
   if (ctx->profiling) {
     CU(ctx, cudaEventRecord(ctx->pev[4], ctx->stream));
     ctx->prof_pending = 1;
   }
-  return FSB_OK;
-}
-
-static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const fsb_params *prm, const fsb_map *map,
-                        int h, int w, int col_begin, int col_end, uint32_t *out_dev, int64_t row_stride,
-                        int64_t pose_stride) {
-  return render_poses_on(ctx, 0, 0, cams, n, prm, map, h, w, col_begin, col_end, out_dev, row_stride, pose_stride);
-}
-
-/* every expand still in flight on the expand stream becomes a dependency of ctx->stream */
-static int join_expand_stream(fsb_context *ctx) {
-  for (int i = 0; i < 2; ++i)
-    if (ctx->sc[i].busy) {
-      CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->sc[i].expanded, 0));
-      ctx->sc[i].busy = 0;
-    }
   return FSB_OK;
 }
 
@@ -900,21 +842,12 @@ int fsb_render_batch_device(fsb_context *ctx, const fsb_camera *cams, int n, con
   if (rc) return rc;
   CU(ctx, cudaSetDevice(ctx->device));
   const int64_t frame = (int64_t)h * w;
-  int g = group_size(n, w, h);
-  /* Overlap mode: launch groups of `overlap_poses` alternate between the two scratch sets; the expand of a group (DRAM-
-   * bound frame stores) runs on the expand stream beside the march + colour pass of the next group (issue-bound). */
-  const int ov = ctx->overlap_poses > 0 && !ctx->profiling && n >= 2 * ctx->overlap_poses;
-  if (ov && ctx->overlap_poses < g) g = ctx->overlap_poses;
-  int it = 0;
-  for (int i = 0; i < n; i += g, ++it) {
+  const int g = group_size(n, w, h);
+  for (int i = 0; i < n; i += g) {
     int c = n - i < g ? n - i : g;
-    if ((rc = render_poses_on(ctx, ov ? (it & 1) : 0, ov, cams + i, c, prm, map, h, w, 0, w, out_dev + (size_t)i * frame, w,
-                              frame))) {
-      join_expand_stream(ctx);
-      return rc;
-    }
+    if ((rc = render_poses(ctx, cams + i, c, prm, map, h, w, 0, w, out_dev + (size_t)i * frame, w, frame))) return rc;
   }
-  return join_expand_stream(ctx);
+  return FSB_OK;
 }
 
 static int ensure_frame(fsb_context *ctx, int slot, size_t pixels) {
