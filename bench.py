@@ -431,6 +431,17 @@ def measure(torch, F, O, ctx, st, flush, wl, wl_key, m, col, hgt, mp, P, steps, 
            "d2h_bytes_per_step": P * frame_bytes, "steps": e_steps, "ms_per_step": 1e3 * e_dt / e_steps,
            "d2h_gb_per_s_aggregate": total * frame_bytes * e_steps / e_dt / 1e9,
            "api": "fsb_render_batch (pinned host frames; pose constants H2D + frames D2H inside the timed region)"}
+    # what the host side can take at all: the same bytes as plain D2H copies, no rendering, all ranks at once
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.copy_to_host(host, out_dev, P * frame_bytes)
+    ctx.sync()
+    c_dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e["d2h_copy_only_gb_per_s_aggregate"] = 3.0 * total * frame_bytes / c_dt / 1e9
+    e2e["note"] = ("d2h_copy_only_* = plain cudaMemcpyAsync of the same frames into the same pinned buffers on every rank at "
+                   "once: the ceiling of the host path (PCIe link per GPU at N = 1, the host's memory / root complex beyond)")
     # the host frames of the last e2e step are checked too (first and last pose)
     import ctypes
     hv = np.ctypeslib.as_array(ctypes.cast(host, ctypes.POINTER(ctypes.c_uint32)), shape=(P, h, w))

@@ -541,6 +541,7 @@ static int grow(fsb_context *ctx, void **ptr, size_t *cap, size_t need) {
 typedef struct {
   int mem;        /* FSB_MEM_* */
   int cols;       /* column-parallel march (fsb_march_cols.cu) */
+  int frame;      /* one CTA per column (fsb_march_frame.cu): single frames, small batches */
   int rec4;       /* 4-byte records */
   int cand_cap;   /* candidate words per column */
   int slice_len;  /* colour pass: records per warp (0: whole lists) */
@@ -715,6 +716,13 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (env && atoi(env) >= 0) min_warps = atoi(env);
     if (warps < min_warps) pl.cols = 0;
   }
+  if (!pl.cols && pl.mem == FSB_MEM_TEX && !(prm->flags & FSB_FLAG_MARCH_Z) && !ctx->force_march_z) {
+    /* too few columns to fill the device with one warp each: four warps per column (measured crossover) */
+    long long max_cols = (long long)ctx->sm_count * 40;
+    const char *env = getenv("FSB_FRAME_MAX_COLS"); /* tuning aid */
+    if (env && atoi(env) >= 0) max_cols = atoi(env);
+    pl.frame = (long long)ncols * n < max_cols;
+  }
   if (pl.cols) {
     pl.cand_cap = max_nz < h ? max_nz : h; /* one candidate per depth sample at most, and rows strictly decrease */
     if (pl.cand_cap < 1) pl.cand_cap = 1;
@@ -789,7 +797,8 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
     CU(ctx, (cudaError_t)fsb_launch_colour(&a, pl.slice_len, ctx->stream, &ctx->launches));
   } else {
-    CU(ctx, (cudaError_t)fsb_launch_march(&a, pl.mem, ctx->stream, &ctx->launches));
+    if (pl.frame) CU(ctx, (cudaError_t)fsb_launch_march_frame(&a, ctx->stream, &ctx->launches));
+    else CU(ctx, (cudaError_t)fsb_launch_march(&a, pl.mem, ctx->stream, &ctx->launches));
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
   }
   if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[3], ctx->stream));

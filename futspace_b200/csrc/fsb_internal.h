@@ -81,6 +81,8 @@ int fsb_launch_setup(const fsb_frame_consts *fc_dev, const fsb_frame_consts *sin
 #define FSB_MEM_TEX 2
 int fsb_launch_march(const fsb_render_args *a, int mem, void *stream, int64_t *launches);
 int fsb_launch_expand(const fsb_render_args *a, void *stream, int64_t *launches);
+/* march of single frames and small batches on the texture path: one CTA per column, four warps over its chunks (fsb_march_frame.cu) */
+int fsb_launch_march_frame(const fsb_render_args *a, void *stream, int64_t *launches);
 /* column-parallel march of the texture path (fsb_march_cols.cu) */
 int fsb_launch_march_cols(const fsb_render_args *a, void *stream, int64_t *launches);
 /* colour pass: candidate lists -> the records fsb_launch_expand consumes; slice_len: records per warp (0: whole lists) */

@@ -680,3 +680,36 @@ def test_config5_16384_map_column_slabs_against_the_oracle(fsb, oracle, gpu_ctx)
     assert not host[:, :b[3]].any() and not host[:, b[4]:].any()      # nothing outside the slab was touched
     gpu_ctx.device_free(dev)
     mp.free()
+
+
+@pytest.mark.parametrize("max_cols", ["0", "100000000"], ids=["one_warp_per_column", "four_warps_per_column"])
+def test_single_frame_march_variants(fsb, oracle, gpu_ctx, fbm1024, monkeypatch, max_cols):
+    """Single frames on the texture path march with four warps per column (fsb_march_frame.cu) below a size threshold
+    and with one warp per column (fsb_march_kernel) above it; FSB_FRAME_MAX_COLS moves the threshold.  Both against the
+    oracle: filters, sentinels, smoothing, full evaluation, ragged and degenerate sizes, short and long series, a batch."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    monkeypatch.setenv("FSB_FRAME_MAX_COLS", max_cols)
+    for filt in (1, 0):
+        for sentinel in (0, 1):
+            for flags in (0, fsb.FLAG_NO_CULL):
+                prm = fsb.default_params(filter=filt, sentinel=sentinel, flags=flags)
+                for p in POSES[:6]:
+                    check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), prm, 300, 417)
+    for p in POSES[:4]:
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*p, SKY), fsb.default_params(flags=fsb.FLAG_SMOOTHING), 257, 95)
+    prm = fsb.default_params()
+    cam = fsb.Camera(512.37, 512.73, 180, 2.2, 40, 300, 1.2, SKY)
+    for h, w in ((1, 1), (7, 5), (33, 9), (257, 8)):
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, h, w)
+    for dist in (0.0004, 0.001, 0.6, 2.0, 5.0, 30.0, 60000.0):   # n_z = 0, 1, 35, 63, 100, 245, 10954
+        cam.distance = dist
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, 64, 48)
+    cam = fsb.Camera(512.37, 512.73, 400, 2.2, 20, 900, 1.2, SKY)   # camera above the terrain: the skipped prefix
+    check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, 200, 333)
+    cams = camera_path(fsb, 1024, 3, 700)
+    frames = gpu_ctx.render_batch(cams, prm, mp, 135, 240)
+    for c, got in zip(cams, frames):
+        assert np.array_equal(got, oracle.render(ocam(oracle, c), oprm(oracle, prm), col, hgt & 0xFF, 135, 240))
+    check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(512, 800, 78, 0, 100, 800, 1, SKY), fsb.tests_variant_params(), 400, 800)
+    mp.free()
