@@ -31,8 +31,8 @@ WORKLOADS = {
     "1080p": dict(map=2048, w=1920, h=1080, dist=2000.0, poses=512, ref_poses=32,
                   name="1920x1080, 2048^2 synthetic fBm terrain, draw distance 2000, 512-pose camera path per GPU"),
     # BASELINE.json configs[2]
-    "4k": dict(map=4096, w=3840, h=2160, dist=4000.0, poses=64, ref_poses=8,
-               name="3840x2160, 4096^2 synthetic fBm terrain, draw distance 4000, 64-pose camera path per GPU"),
+    "4k": dict(map=4096, w=3840, h=2160, dist=4000.0, poses=128, ref_poses=8,
+               name="3840x2160, 4096^2 synthetic fBm terrain, draw distance 4000, 128-pose camera path per GPU"),
     # BASELINE.json configs[4]: one frame cut into column slabs, one slab per GPU, assembled on rank 0
     "8k-colsplit": dict(map=16384, w=7680, h=4320, dist=4000.0, poses=1, ref_poses=1, colsplit=True,
                         name="7680x4320 single frame, 16384^2 synthetic fBm terrain replicated per GPU, distance 4000, "

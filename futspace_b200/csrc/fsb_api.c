@@ -717,8 +717,9 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (warps < min_warps) pl.cols = 0;
   }
   if (!pl.cols && pl.mem == FSB_MEM_TEX && !(prm->flags & FSB_FLAG_MARCH_Z) && !ctx->force_march_z) {
-    /* too few columns to fill the device with one warp each: four warps per column (measured crossover) */
-    long long max_cols = (long long)ctx->sm_count * 40;
+    /* too few columns to fill the device with one warp each: four warps per column.  Measured (round 2,
+     * profiles/r2_single_frame_march_variants.jsonl): 37 -> 31 us for a lone 1920-column frame, a loss from 3840 columns on */
+    long long max_cols = (long long)ctx->sm_count * 16;
     const char *env = getenv("FSB_FRAME_MAX_COLS"); /* tuning aid */
     if (env && atoi(env) >= 0) max_cols = atoi(env);
     pl.frame = (long long)ncols * n < max_cols;
