@@ -81,6 +81,9 @@ int fsb_launch_setup(const fsb_frame_consts *fc_dev, const fsb_frame_consts *sin
 #define FSB_MEM_TEX 2
 int fsb_launch_march(const fsb_render_args *a, int mem, void *stream, int64_t *launches);
 int fsb_launch_expand(const fsb_render_args *a, void *stream, int64_t *launches);
+/* expand of 4-byte records with TMA tile stores (fsb_expand_tma.cu); applicable: base and strides 16-byte aligned */
+int fsb_expand_tma_applicable(const fsb_render_args *a);
+int fsb_launch_expand_tma(const fsb_render_args *a, void *stream, int64_t *launches);
 /* march of single frames and small batches on the texture path: one CTA per column, four warps over its chunks (fsb_march_frame.cu) */
 int fsb_launch_march_frame(const fsb_render_args *a, void *stream, int64_t *launches);
 /* column-parallel march of the texture path (fsb_march_cols.cu) */
