@@ -70,13 +70,24 @@ while time.time() - t0 < budget:
         prm.filter = int(rng.integers(0, 2))
         prm.sentinel = int(rng.integers(0, 2))
         prm.f2i_mode = int(rng.choice([0, 0, 0, 1, 2]))
-        prm.flags = int(rng.choice([0, 0, 0, 1, 2, 4, 8, 9, 10, 12]))
+        prm.flags = int(rng.choice([0, 0, 0, 1, 2, 4, 8, 9, 10, 12, 16, 20, 24]))
         if prm.flags & 8:
             prm.sentinel = 0
         if rng.random() < 0.2:
             prm.invz_param1, prm.invz_param2 = float(rng.uniform(-1.0, 3.0)), float(rng.uniform(1, 600))
         if rng.random() < 0.15:
             prm.z0, prm.delta = float(rng.uniform(-1.0, 3.0)), float(rng.uniform(0.0005, 0.05))
+        # round 2: which march / colour-pass shape renders it (read per call by the library)
+        for k in ("FSB_COLS_MIN_WARPS", "FSB_COLOUR_SLICE", "FSB_FRAME_MAX_COLS"):
+            os.environ.pop(k, None)
+        v = int(rng.integers(0, 5))
+        if v == 0:
+            os.environ["FSB_COLS_MIN_WARPS"] = "0"
+            os.environ["FSB_COLOUR_SLICE"] = str(int(rng.choice([0, 1, 5, 32])))
+        elif v == 1:
+            os.environ["FSB_FRAME_MAX_COLS"] = "0"
+        elif v == 2:
+            os.environ["FSB_FRAME_MAX_COLS"] = "100000000"
         mode = int(rng.integers(0, 4))   # which entry point produces the frame
         try:
             if mode == 0:
