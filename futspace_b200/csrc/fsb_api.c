@@ -53,6 +53,7 @@ struct fsb_context {
   int force_rec8;                 /* env FSB_REC8: always 8-byte records */
   const float *lut;               /* device address of the colour look-up table */
   int force_march_z;              /* env FSB_MARCH_Z: always the lanes-over-depth march */
+  int no_pdl;                     /* env FSB_PDL=0: no programmatic dependent launch for single frames */
   char name[128];
 };
 
@@ -184,6 +185,7 @@ int fsb_context_new(int device, fsb_context **out) {
   ctx->device = device;
   ctx->force_rec8 = getenv("FSB_REC8") != NULL;
   ctx->force_march_z = getenv("FSB_MARCH_Z") != NULL;
+  ctx->no_pdl = getenv("FSB_PDL") != NULL && atoi(getenv("FSB_PDL")) == 0;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   ctx->sm_count = prop.multiProcessorCount;
   snprintf(ctx->name, sizeof ctx->name, "%.127s", prop.name);
@@ -789,6 +791,8 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.rec4 = pl.rec4;
   a.full_eval = (prm->flags & FSB_FLAG_NO_CULL) ? 1 : 0;
   a.lut = ctx->lut;
+  /* single frames: the three dependent launches overlap their scheduling (programmatic dependent launch); FSB_PDL=0: off */
+  a.pdl = n == 1 && !pl.cols && !ctx->no_pdl;
   a.cand = sc->cand;
   a.cand_cnt = sc->cand_cnt;
   a.cand_cap = pl.cand_cap;

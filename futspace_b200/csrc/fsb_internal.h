@@ -68,6 +68,7 @@ typedef struct fsb_render_args {
   int32_t ncols_pad;        /* columns rounded up to a multiple of 32                                         */
   int32_t full_eval;        /* FSB_FLAG_NO_CULL: also no early exit when the y-buffer reaches row 0           */
   const float *lut;         /* c/255 [0..255] and its square [256..511] (device, filled once per device)      */
+  int32_t pdl;              /* single frames: march and expand are launched with programmatic stream serialization */
 } fsb_render_args;
 
 /* launchers implemented in fsb_kernels.cu; stream is a cudaStream_t passed as void*.

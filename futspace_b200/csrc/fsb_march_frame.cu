@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(M4_WARPS * 32) fsb_march4_kernel(const fsb_ren
   const float *un = a.lut, *sq = a.lut + 256;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pose = blockIdx.y, jrel = blockIdx.x;
+  pdl_trigger();
+  pdl_wait(); /* depth table and pose constants come from the set-up kernel */
   const int ncols = a.col_end - a.col_begin;
   const fsb_frame_consts *fcp = a.fc + pose;
   const float cam_h = fcp->cam_h, horizon = fcp->horizon, cull_d = fcp->cull_d;
@@ -193,10 +195,8 @@ __global__ void __launch_bounds__(M4_WARPS * 32) fsb_march4_kernel(const fsb_ren
 extern "C" int fsb_launch_march_frame(const fsb_render_args *a, void *stream, int64_t *launches) {
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(a->col_end - a->col_begin, a->n_poses);
-  if (a->filter == FSB_FILTER_BILINEAR)
-    fsb_march4_kernel<true><<<grid, M4_WARPS * 32, 0, s>>>(*a);
-  else
-    fsb_march4_kernel<false><<<grid, M4_WARPS * 32, 0, s>>>(*a);
   if (launches) ++*launches;
-  return (int)cudaGetLastError();
+  if (a->filter == FSB_FILTER_BILINEAR)
+    return (int)fsb_launch_pdl(fsb_march4_kernel<true>, grid, dim3(M4_WARPS * 32), s, a->pdl != 0, *a);
+  return (int)fsb_launch_pdl(fsb_march4_kernel<false>, grid, dim3(M4_WARPS * 32), s, a->pdl != 0, *a);
 }
