@@ -67,6 +67,8 @@ struct fsb_map {
   int pow2, log2r;
   uint32_t alpha_bits;
   int32_t hmax;                   /* highest (masked) terrain height */
+  uint8_t *hpyr;                  /* device: pyramid of local height maxima for the local occlusion bound (build_height_pyramid), or NULL */
+  int pyr_levels;
 };
 
 static int set_err(fsb_context *ctx, int code, const char *fmt, ...) {
@@ -271,6 +273,59 @@ static uint16_t half_bits_of_byte(uint32_t v) {
   return (uint16_t)(((e + 15) << 10) | (((v << (10 - e)) & 0x3FF)));
 }
 
+/* Pyramid of local height maxima for the march's local occlusion bound (fsb_march_cols.cu, chunk_hidden): level L
+ * (1..levels) holds, for every 2^L x 2^L block of texels, the highest texel of the 2 x 2 blocks starting at it (wrapped
+ * like the samplers wrap) -- any rectangle of at most 2^L texels a side lies inside one such 2 x 2 neighbourhood, so ONE
+ * byte bounds every height a group of samples can read.  Power-of-two maps with heights 0..255; level L at byte offset
+ * (q r - (q r >> (2L - 2))) / 3, row-major (q >> L) x (r >> L). */
+static uint8_t *build_height_pyramid(const int32_t *hm, int q, int r, int *levels_out, size_t *bytes_out) {
+  int levels = 0;
+  while ((2 << levels) <= q && (2 << levels) <= r) ++levels;
+  if (levels < 1) return NULL;
+  const size_t n = (size_t)q * r;
+  uint8_t *prev = (uint8_t *)malloc(n), *out = (uint8_t *)malloc(n / 3 + 16);
+  if (!prev || !out) {
+    free(prev); free(out);
+    return NULL;
+  }
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; ++i) prev[i] = (uint8_t)hm[i];
+  int pq = q, pr = r;
+  for (int L = 1; L <= levels; ++L) {
+    const int cq = pq >> 1, cr = pr >> 1;
+    uint8_t *cur = (uint8_t *)malloc((size_t)cq * cr);
+    if (!cur) {
+      free(prev); free(out);
+      return NULL;
+    }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < cq; ++y)
+      for (int x = 0; x < cr; ++x) {
+        const uint8_t *a = prev + (size_t)(2 * y) * pr + 2 * x, *b = a + pr;
+        uint8_t v = a[0] > a[1] ? a[0] : a[1], w = b[0] > b[1] ? b[0] : b[1];
+        cur[(size_t)y * cr + x] = v > w ? v : w;
+      }
+    uint8_t *dst = out + (n - (n >> (2 * L - 2))) / 3;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < cq; ++y) {
+      const uint8_t *a = cur + (size_t)y * cr, *b = cur + (size_t)((y + 1) & (cq - 1)) * cr;
+      for (int x = 0; x < cr; ++x) {
+        const int x1 = (x + 1) & (cr - 1);
+        uint8_t v = a[x] > a[x1] ? a[x] : a[x1], w = b[x] > b[x1] ? b[x] : b[x1];
+        dst[(size_t)y * cr + x] = v > w ? v : w;
+      }
+    }
+    free(prev);
+    prev = cur;
+    pq = cq;
+    pr = cr;
+  }
+  free(prev);
+  *levels_out = levels;
+  *bytes_out = (n - (n >> (2 * levels))) / 3;
+  return out;
+}
+
 int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, int q, int r, int mask_heights,
                 fsb_map **out) {
   if (!ctx) return FSB_ERR_ARG;
@@ -387,7 +442,18 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->color, color, n * 4, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->height, hm, n * 4, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess && m->packed) e = cudaMemcpyAsync(m->packed, pk, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+  uint8_t *pyr_host = NULL;
+  if (e == cudaSuccess && m->tex_h && m->pow2 && n <= ((size_t)1 << 30)) {
+    /* optional: without it the march only has the map-wide bound */
+    size_t pyr_bytes = 0;
+    pyr_host = build_height_pyramid(hm, q, r, &m->pyr_levels, &pyr_bytes);
+    if (pyr_host && cudaMalloc((void **)&m->hpyr, pyr_bytes) == cudaSuccess)
+      e = cudaMemcpyAsync(m->hpyr, pyr_host, pyr_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    else
+      (void)cudaGetLastError();
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  free(pyr_host);
   free(hm);
   free(pk);
   free(pk_rm);
@@ -397,7 +463,7 @@ int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, 
     if (m->tex_f) cudaDestroyTextureObject(m->tex_f);
     if (m->array) cudaFreeArray(m->array);
     if (m->array_h) cudaFreeArray(m->array_h);
-    cudaFree(m->color); cudaFree(m->height); cudaFree(m->packed);
+    cudaFree(m->color); cudaFree(m->height); cudaFree(m->packed); cudaFree(m->hpyr);
     free(m);
     (void)cudaGetLastError();
     return set_err(ctx, FSB_ERR_CUDA, "fsb_map_new: %s", cudaGetErrorString(e));
@@ -463,6 +529,7 @@ int fsb_map_free(fsb_context *ctx, fsb_map *m) {
   cudaFree(m->color);
   cudaFree(m->height);
   cudaFree(m->packed);
+  cudaFree(m->hpyr);
   free(m);
   return FSB_OK;
 }
@@ -542,7 +609,8 @@ static int grow(fsb_context *ctx, void **ptr, size_t *cap, size_t need) {
 /* How one launch group is rendered: which march, which record format, how the depth series is split. */
 typedef struct {
   int mem;        /* FSB_MEM_* */
-  int cols;       /* column-parallel march (fsb_march_cols.cu) */
+  int cols;       /* column-parallel lists: fsb_march_cols.cu, or fsb_march_split.cu when `split` */
+  int split;      /* depth-parallel cluster march (fsb_march_split.cu): warps per group of 32 columns (32 / 64), 0: off */
   int frame;      /* one CTA per column (fsb_march_frame.cu): single frames, small batches */
   int rec4;       /* 4-byte records */
   int cand_cap;   /* candidate words per column */
@@ -718,6 +786,26 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (env && atoi(env) >= 0) min_warps = atoi(env);
     if (warps < min_warps) pl.cols = 0;
   }
+  const char *env_split = getenv("FSB_SPLIT"); /* A/B and tests: FSB_SPLIT=0 keeps the marches of fsb_march_frame.cu / fsb_kernels.cu */
+  if (!pl.cols && pl.mem == FSB_MEM_TEX && max_nz <= FSB_COLS_MAX_NZ && !(prm->flags & FSB_FLAG_MARCH_Z) && !ctx->force_march_z &&
+      !(env_split && atoi(env_split) == 0)) {
+    /* Too few groups of 32 columns to fill the device with one warp each (single frames, small batches): the depth series
+     * of every group is split over the 32 or 64 warps of a thread-block cluster (fsb_march_split.cu), 64 while the whole
+     * launch still fits the device at 32 warps per SM. */
+    const long long groups = (long long)(pl.ncols_pad / 32) * n;
+    const int n_chunks = (max_nz + 31) / 32;
+    int wpg = groups * 64 <= (long long)ctx->sm_count * 32 ? 64 : 32;
+    const char *env = getenv("FSB_SPLIT_WARPS"); /* tuning aid */
+    if (env && (atoi(env) == 32 || atoi(env) == 64)) wpg = atoi(env);
+    long long max_groups = (long long)ctx->sm_count * 4;
+    env = getenv("FSB_SPLIT_MAX_GROUPS"); /* tuning aid */
+    if (env && atoi(env) >= 0) max_groups = atoi(env);
+    if (n_chunks > fsb_march_split_max_chunks(wpg)) wpg = 64;
+    if (n_chunks <= fsb_march_split_max_chunks(wpg) && groups <= max_groups) {
+      pl.split = wpg;
+      pl.cols = 1;
+    }
+  }
   if (!pl.cols && pl.mem == FSB_MEM_TEX && !(prm->flags & FSB_FLAG_MARCH_Z) && !ctx->force_march_z) {
     /* too few columns to fill the device with one warp each: four warps per column.  Measured (round 2,
      * profiles/r2_single_frame_march_variants.jsonl): 37 -> 31 us for a lone 1920-column frame, a loss from 3840 columns on */
@@ -732,6 +820,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     /* colour pass: whole lists per warp when there are plenty of them, otherwise slices of 32 records */
     const long long lists = (long long)(pl.ncols_pad / 32) * n;
     pl.slice_len = lists >= (long long)ctx->sm_count * 160 ? 0 : lists >= (long long)ctx->sm_count * 80 ? 64 : 32;
+    if (pl.split) pl.slice_len = 8; /* a lone frame has 60 lists of 32 columns: short slices spread the filter over the device */
     const char *env = getenv("FSB_COLOUR_SLICE");
     if (env && atoi(env) >= 0) pl.slice_len = atoi(env);
   }
@@ -746,8 +835,9 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (prc) return prc;
     CU(ctx, cudaEventRecord(ctx->pev[0], ctx->stream));
   }
-  CU(ctx, (cudaError_t)fsb_launch_setup(sc->fc_dev, n == 1 ? &single : NULL, n, sc->table, tab_stride,
-                                        ctx->stream, &ctx->launches));
+  if (!pl.split) /* the depth-parallel march builds its own table entries */
+    CU(ctx, (cudaError_t)fsb_launch_setup(sc->fc_dev, n == 1 ? &single : NULL, n, sc->table, tab_stride,
+                                          ctx->stream, &ctx->launches));
   if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[1], ctx->stream));
   fsb_render_args a;
   memset(&a, 0, sizeof a);
@@ -792,13 +882,24 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.full_eval = (prm->flags & FSB_FLAG_NO_CULL) ? 1 : 0;
   a.lut = ctx->lut;
   /* single frames: the three dependent launches overlap their scheduling (programmatic dependent launch); FSB_PDL=0: off */
-  a.pdl = n == 1 && !pl.cols && !ctx->no_pdl;
+  a.pdl = (pl.split || (n == 1 && !pl.cols)) && !ctx->no_pdl;
+  {
+    const char *env = getenv("FSB_LOCAL_CULL"); /* A/B: FSB_LOCAL_CULL=0 keeps only the map-wide occlusion bound */
+    if (map->hpyr && !(env && atoi(env) == 0)) {
+      a.hpyr = map->hpyr;
+      a.pyr_levels = map->pyr_levels;
+    }
+  }
   a.cand = sc->cand;
   a.cand_cnt = sc->cand_cnt;
   a.cand_cap = pl.cand_cap;
   a.ncols_pad = pl.ncols_pad;
   if (pl.cols) {
-    CU(ctx, (cudaError_t)fsb_launch_march_cols(&a, ctx->stream, &ctx->launches));
+    if (pl.split)
+      CU(ctx, (cudaError_t)fsb_launch_march_split(&a, n == 1 ? &single : NULL, pl.split, (max_nz + 31) / 32, ctx->stream,
+                                                  &ctx->launches));
+    else
+      CU(ctx, (cudaError_t)fsb_launch_march_cols(&a, ctx->stream, &ctx->launches));
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
     CU(ctx, (cudaError_t)fsb_launch_colour(&a, pl.slice_len, ctx->stream, &ctx->launches));
   } else {

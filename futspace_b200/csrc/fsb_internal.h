@@ -68,7 +68,9 @@ typedef struct fsb_render_args {
   int32_t ncols_pad;        /* columns rounded up to a multiple of 32                                         */
   int32_t full_eval;        /* FSB_FLAG_NO_CULL: also no early exit when the y-buffer reaches row 0           */
   const float *lut;         /* c/255 [0..255] and its square [256..511] (device, filled once per device)      */
-  int32_t pdl;              /* single frames: march and expand are launched with programmatic stream serialization */
+  const uint8_t *hpyr;      /* pyramid of local height maxima (fsb_api.c build_height_pyramid), or NULL: no local occlusion bound */
+  int32_t pyr_levels;
+  int32_t pdl;              /* single frames: march / colour / expand are launched with programmatic stream serialization */
 } fsb_render_args;
 
 /* launchers implemented in fsb_kernels.cu; stream is a cudaStream_t passed as void*.
@@ -87,6 +89,11 @@ int fsb_expand_tma_applicable(const fsb_render_args *a);
 int fsb_launch_expand_tma(const fsb_render_args *a, void *stream, int64_t *launches);
 /* march of single frames and small batches on the texture path: one CTA per column, four warps over its chunks (fsb_march_frame.cu) */
 int fsb_launch_march_frame(const fsb_render_args *a, void *stream, int64_t *launches);
+/* depth-parallel march of single frames and small batches on the texture path (fsb_march_split.cu): one cluster of 8 CTAs per
+ * group of 32 columns, warps_per_group (32 or 64) depth segments; no set-up launch (single != NULL: the one pose's constants) */
+int fsb_march_split_max_chunks(int warps_per_group);
+int fsb_launch_march_split(const fsb_render_args *a, const fsb_frame_consts *single, int warps_per_group, int n_chunks_max,
+                           void *stream, int64_t *launches);
 /* column-parallel march of the texture path (fsb_march_cols.cu) */
 int fsb_launch_march_cols(const fsb_render_args *a, void *stream, int64_t *launches);
 /* colour pass: candidate lists -> the records fsb_launch_expand consumes; slice_len: records per warp (0: whole lists) */

@@ -29,49 +29,6 @@
 
 #define FSB_MC_WARPS 4 /* warps (= groups of 32 columns) per march CTA */
 
-/* One depth step of one column: the four heights of the bilinear footprint (or the single nearest height in h00) and
- * the weights, fut/render_functions.fut:67-77 / :63-64.  Kept in registers between the gather and its use. */
-template <bool BIL>
-struct col_step {
-  float h00, h01, h10, h11;
-  float wx0, wx1, wy0, wy1;
-};
-
-/* get_segment (fut/voxel_renderer.fut:63-66) + the gather of png_height(_filtered).
- * Bilinear weights: wx1 = x - floor x as written.  wx0 = ceil x - x without a second FRND on the XU pipe:
- * ceil x = floor x + (x > floor x ? 1 : 0), exact below 2^23 -- one FSET.  The same corner addresses the gather: for a
- * non-integer x it is floor x + 1, the common corner of the footprint {floor, floor + 1} (see FSB_TLD4); for an integer x
- * both weights are 0, every product is +0 (heights are 0..255) and the texels fetched do not reach the result
- * (SURVEY.md fact 9), so the footprint may be anything. */
-template <bool BIL>
-__device__ __forceinline__ void cstep_issue(col_step<BIL> &t, const fsb_render_args &a, const float4 l, float fj) {
-  const float x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
-  const float y = __fadd_rn(l.y, __fmul_rn(fj, l.w));
-  if (BIL) {
-    const float fx = floorf(x), fy = floorf(y);
-    t.wx1 = __fsub_rn(x, fx);
-    t.wy1 = __fsub_rn(y, fy);
-    const float cx = __fadd_rn(fx, t.wx1 > 0.0f ? 1.0f : 0.0f), cy = __fadd_rn(fy, t.wy1 > 0.0f ? 1.0f : 0.0f);
-    FSB_TLD4_F32(a.tex_h, __fmul_rn(cx, a.inv_r), __fmul_rn(cy, a.inv_q), t.h10, t.h11, t.h01, t.h00);
-    t.wx0 = __fsub_rn(cx, x);
-    t.wy0 = __fsub_rn(cy, y);
-  } else { /* i32.f32 truncates toward zero, then floored modulo = the texture unit's wrap (fut/render_functions.fut:63-64) */
-    const float u = __fmul_rn(__fadd_rn(truncf(x), 0.5f), a.inv_r), v = __fmul_rn(__fadd_rn(truncf(y), 0.5f), a.inv_q);
-    float g, b, al;
-    asm volatile("tex.2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6}];"
-                 : "=f"(t.h00), "=f"(g), "=f"(b), "=f"(al)
-                 : "l"(a.tex_h), "f"(u), "f"(v));
-  }
-}
-
-template <bool BIL>
-__device__ __forceinline__ float cstep_height(const col_step<BIL> &t) {
-  if (!BIL) return t.h00;
-  const float xi1 = __fadd_rn(__fmul_rn(t.wx0, t.h00), __fmul_rn(t.wx1, t.h01));
-  const float xi2 = __fadd_rn(__fmul_rn(t.wx0, t.h10), __fmul_rn(t.wx1, t.h11));
-  return __fadd_rn(__fmul_rn(t.wy0, xi1), __fmul_rn(t.wy1, xi2));
-}
-
 /* Per-lane march state: the y-buffer of :231 as a float (exact: rows <= 32768; -inf once it reached row 0 -- y >= 0
  * always, :225, so nothing can pass `y < 0` any more) and the append pointer of the column's candidate list. */
 struct col_state {
@@ -105,11 +62,50 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-/* Scratch layout of this file (and of the expand kernels behind it, list_view in fsb_kernels.cu): the lists of the 32
- * columns of a group are interleaved -- entry p of lane l at (p * 32 + l) words from the group's base -- because every
- * kernel here has lane = column: appends of neighbouring columns share 128-byte lines instead of touching 32. */
-__device__ __forceinline__ size_t cand_group_base(const fsb_render_args &a, int pose, int group) {
-  return ((size_t)pose * (a.ncols_pad >> 5) + group) * a.cand_cap * 32;
+/* Local occlusion bound.  The map-wide bound (fsb_kernels.cu) ends a column once NO terrain could rise above its
+ * y-buffer; most of what a low camera does not see is hidden behind a nearby ridge long before that.  Per chunk of 32 depth
+ * steps and group of 32 columns the warp asks whether the terrain under THIS block of samples can reach any of its 32
+ * y-buffers: lane (s, b) takes the sub-block of steps 4s..4s+3 x columns 8b..8b+7, whose sample positions lie inside the
+ * bounding box of its four corner samples (positions are monotone in the column index along a line and move along a ray
+ * from the camera with depth); the box, widened by the bilinear footprint and two texels of rounding slack, spans at most
+ * 2^L texels a side, and ONE byte of the level-L pyramid (fsb_api.c build_height_pyramid) bounds every texel it can
+ * touch.  No sample of the sub-block is higher than that + 0.5 (see the map-wide bound), so none projects above
+ * row(bound) -- every operation of :223-225 is monotone, and inv_z decreases along the series (bound at the sub-block's last
+ * step for a camera above the local maximum, at its first step below it).  The chunk is skipped when every column's
+ * y-buffer is at or above the lowest such row of its eight columns: nothing in it can pass `occlude` (strict <), the
+ * frame is unchanged.  About 70 instructions against the 1250 of an evaluated chunk. */
+__device__ __forceinline__ bool chunk_hidden(const fsb_render_args &a, const float4 *tl, const float *tz, float fj0, int lane,
+                                             float cam_h, float horizon, float ybuf_f) {
+  const int s4 = (lane >> 2) * 4;
+  const float4 l0 = tl[s4], l1 = tl[s4 + 3];
+  const float ja = fj0 + (float)((lane & 3) * 8), jb = ja + 7.0f;
+  const float xa0 = l0.x + ja * l0.z, xb0 = l0.x + jb * l0.z, xa1 = l1.x + ja * l1.z, xb1 = l1.x + jb * l1.z;
+  const float ya0 = l0.y + ja * l0.w, yb0 = l0.y + jb * l0.w, ya1 = l1.y + ja * l1.w, yb1 = l1.y + jb * l1.w;
+  const float mag = fabsf(xa0) + fabsf(xb0) + fabsf(xa1) + fabsf(xb1) + fabsf(ya0) + fabsf(yb0) + fabsf(ya1) + fabsf(yb1);
+  int bound = -1; /* hides nothing (a finished column's y-buffer is -inf) */
+  if (mag < 3.2e7f) { /* finite and within the texture path's coordinate range (a NaN fails the test) */
+    const int x0 = __float2int_rd(fminf(fminf(xa0, xb0), fminf(xa1, xb1))) - 2;
+    const int x1 = __float2int_rd(fmaxf(fmaxf(xa0, xb0), fmaxf(xa1, xb1))) + 3;
+    const int y0 = __float2int_rd(fminf(fminf(ya0, yb0), fminf(ya1, yb1))) - 2;
+    const int y1 = __float2int_rd(fmaxf(fmaxf(ya0, yb0), fmaxf(ya1, yb1))) + 3;
+    const int ext = max(x1 - x0, y1 - y0) + 1; /* texels a side, >= 6 */
+    const int L = 32 - __clz(ext - 1);         /* 2^L >= ext */
+    if (L <= a.pyr_levels) {
+      const int rl = a.r >> L, ql = a.q >> L;
+      const uint32_t qr = (uint32_t)a.q * (uint32_t)a.r;
+      const uint32_t off = (qr - (qr >> (2 * L - 2))) / 3u + (uint32_t)((y0 >> L) & (ql - 1)) * (uint32_t)rl +
+                           (uint32_t)((x0 >> L) & (rl - 1));
+      const float hb = __fadd_ru((float)__ldg(a.hpyr + off), 0.501f);
+      const float d = __fsub_rd(cam_h, hb);
+      const float iz = d >= 0.0f ? tz[s4 + 3] : tz[s4];
+      bound = max(0, __float2int_rz(__fadd_rn(__fmul_rn(d, iz), horizon)));
+    }
+  }
+  bound = min(bound, __shfl_xor_sync(FSB_FULL, bound, 4));
+  bound = min(bound, __shfl_xor_sync(FSB_FULL, bound, 8));
+  bound = min(bound, __shfl_xor_sync(FSB_FULL, bound, 16));
+  const int mine = __shfl_sync(FSB_FULL, bound, lane >> 3); /* lanes 0..3 hold the bounds of columns 0-7, 8-15, 16-23, 24-31 */
+  return __all_sync(FSB_FULL, ybuf_f <= (float)mine);
 }
 
 /* U consecutive inv_z of the staged chunk with the widest shared-memory loads (p is U * 4-byte aligned) */
@@ -136,7 +132,7 @@ __device__ __forceinline__ void load_inv_z(const float *p, float (&iz)[U]) {
  * the CTA (4 warps = 128 adjacent columns of one pose) stages them in shared memory with cp.async, two
  * chunks ahead of the one being marched: the per-step operands are LDS broadcasts (29 cycles) instead of global loads
  * queued behind the texture gathers in the same L1 pipe (round-2 ncu: the largest stall site of the first version). */
-template <bool BIL, int U, int MINB>
+template <bool BIL, int U, int MINB, bool XPF>
 __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(const fsb_render_args a) {
   static_assert(32 % (2 * U) == 0, "a pair of register sets must tile a 32-step chunk");
   __shared__ __align__(16) float sm[3][FSB_TAB_BLOCK];
@@ -197,10 +193,10 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
     cp_async_wait_all();
     __syncthreads();
     col_step<BIL> sa[U], sb[U];
-    if (active) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, reinterpret_cast<const float4 *>(sm[0])[u], fj);
-    }
+    /* sa holds the gathers of the head of the chunk about to be marched (issued at the tail of the chunk before it) */
+    bool have_sa = false;
+    const bool local_cull = a.hpyr != nullptr && cull_d > -INFINITY && cull_d < INFINITY && !a.full_eval;
+    const float fj0 = (float)(a.col_begin + group * 32);
     int slot = 0;
     for (int c = c_first; c < c_end; ++c) {
       const int slot1 = slot == 2 ? 0 : slot + 1, slot2 = slot1 == 2 ? 0 : slot1 + 1;
@@ -214,9 +210,19 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
         if (can_stop) bound = (float)max(0, __float2int_rz(__fadd_rn(__fmul_rn(cull_d, tz[0]), horizon)));
         active = __any_sync(FSB_FULL, st.ybuf_f > bound); /* false: every column of the group is finished, for good */
       }
-      if (active) {
+      bool eval = active;
+      if (active && !have_sa) { /* first chunk, or the chunk before this one was skipped */
+        if (local_cull && chunk_hidden(a, tl, tz, fj0, lane, cam_h, horizon, st.ybuf_f)) eval = false;
+        else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, tl[u], fj);
+        }
+      }
+      have_sa = false;
+      if (eval) {
         ++c_done;
         const float4 *tl_next = reinterpret_cast<const float4 *>(sm[slot1]);
+        const float *tz_next = sm[slot1] + 128;
         const uint32_t kw = (uint32_t)(c << 5) << FSB_ROW_BITS;
 #pragma unroll
         for (int i = 0; i < 32; i += 2 * U) {
@@ -228,10 +234,16 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
 #pragma unroll
           for (int u = 0; u < U; ++u)
             cstep_resolve<BIL>(sa[u], iza[u], cam_h, horizon, kw + ((uint32_t)(i + u) << FSB_ROW_BITS), st);
-          /* next set: the following steps of this chunk, or the head of the next one (a repeated last sample in the
-           * padding projects to the same row and `occlude` keeps the earlier one) */
+          /* next set: the following steps of this chunk, or the head of the next one unless the local bound hides it
+           * (tested with the y-buffers as they are now; they only fall) */
+          if (i + 2 * U < 32) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, i + 2 * U < 32 ? tl[i + 2 * U + u] : tl_next[u], fj);
+            for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, tl[i + 2 * U + u], fj);
+          } else if (XPF && c + 1 < c_end && !(local_cull && chunk_hidden(a, tl_next, tz_next, fj0, lane, cam_h, horizon, st.ybuf_f))) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, tl_next[u], fj);
+            have_sa = true;
+          }
 #pragma unroll
           for (int u = 0; u < U; ++u)
             cstep_resolve<BIL>(sb[u], izb[u], cam_h, horizon, kw + ((uint32_t)(i + U + u) << FSB_ROW_BITS), st);
@@ -318,12 +330,14 @@ __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a
   __shared__ float sq_sm[256]; /* (c/255)^2: the second-stage operands of the three mixes */
   const float *un = a.lut, *sq = a.lut + 256;
   __shared__ uint32_t bias_slot;
+  pdl_trigger(); /* single frames (programmatic dependent launch): the expand kernel may be scheduled */
   sq_sm[threadIdx.x] = sq[threadIdx.x];
   sq_sm[threadIdx.x + 128] = sq[threadIdx.x + 128];
   /* table address minus 0x4B000000 * 4 (see sq_of_bits), passed through shared memory so that ptxas keeps it in one
    * register instead of re-deriving the difference at each of the six look-ups of a record */
   if (threadIdx.x == 0) bias_slot = (uint32_t)__cvta_generic_to_shared(sq_sm) - 0x4B000000u * 4u;
   __syncthreads();
+  pdl_wait(); /* candidate lists, counts and the depth table come from the march */
   const uint32_t sq_sm_biased = *reinterpret_cast<volatile uint32_t *>(&bias_slot);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pose = blockIdx.z;
@@ -397,11 +411,11 @@ __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a
 }
 
 /* ------------------------------------------------------------------------------------------ */
-template <bool BIL, int U, int MINB>
+template <bool BIL, int U, int MINB, bool XPF = true>
 static int launch_marchc_t(const fsb_render_args &a, cudaStream_t s) {
   const int ncols = a.col_end - a.col_begin;
   dim3 grid((ncols + FSB_MC_WARPS * 32 - 1) / (FSB_MC_WARPS * 32), a.n_poses);
-  fsb_marchc_kernel<BIL, U, MINB><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
+  fsb_marchc_kernel<BIL, U, MINB, XPF><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -419,6 +433,7 @@ extern "C" int fsb_launch_march_cols(const fsb_render_args *a, void *stream, int
   else if (bil && variant == 2) rc = launch_marchc_t<true, 2, 8>(*a, s);
   else if (bil && variant == 3) rc = launch_marchc_t<true, 2, 10>(*a, s);
   else if (bil && variant == 4) rc = launch_marchc_t<true, 8, 4>(*a, s);
+  else if (bil && variant == 5) rc = launch_marchc_t<true, 4, 6, false>(*a, s);
   else
     rc = bil ? launch_marchc_t<true, 4, 6>(*a, s) : launch_marchc_t<false, 4, 6>(*a, s);
   if (launches) ++*launches;
@@ -431,13 +446,15 @@ extern "C" int fsb_launch_colour(const fsb_render_args *a, int slice_len, void *
   const int groups = a->ncols_pad >> 5;
   const int slices = slice_len > 0 ? (a->cand_cap + slice_len - 1) / slice_len : 1;
   dim3 grid((groups + 3) / 4, slices, a->n_poses);
+  const bool pdl = a->pdl != 0;
+  int rc;
   if (a->filter == FSB_FILTER_BILINEAR) {
-    if (a->rec4) fsb_colour_kernel<true, true><<<grid, 128, 0, s>>>(*a, slice_len);
-    else fsb_colour_kernel<true, false><<<grid, 128, 0, s>>>(*a, slice_len);
+    if (a->rec4) rc = (int)fsb_launch_pdl(fsb_colour_kernel<true, true>, grid, dim3(128), s, pdl, *a, slice_len);
+    else rc = (int)fsb_launch_pdl(fsb_colour_kernel<true, false>, grid, dim3(128), s, pdl, *a, slice_len);
   } else {
-    if (a->rec4) fsb_colour_kernel<false, true><<<grid, 128, 0, s>>>(*a, slice_len);
-    else fsb_colour_kernel<false, false><<<grid, 128, 0, s>>>(*a, slice_len);
+    if (a->rec4) rc = (int)fsb_launch_pdl(fsb_colour_kernel<false, true>, grid, dim3(128), s, pdl, *a, slice_len);
+    else rc = (int)fsb_launch_pdl(fsb_colour_kernel<false, false>, grid, dim3(128), s, pdl, *a, slice_len);
   }
   if (launches) ++*launches;
-  return (int)cudaGetLastError();
+  return rc;
 }

@@ -48,7 +48,7 @@ def test_tests_variant_golden(fsb, oracle, gpu_ctx, c1w_d1, golden_frames):
     cam = fsb.Camera(512, 800, 78, 0, 100, 800, 1, SKY)
     n0 = gpu_ctx.launch_count
     got = check(fsb, oracle, gpu_ctx, mp, rgb, hgt, cam, fsb.tests_variant_params(), 400, 800)
-    assert gpu_ctx.launch_count - n0 == 3   # set-up, march, expand
+    assert gpu_ctx.launch_count - n0 == 3   # depth-parallel march (builds its own depth table), colour, expand
     assert np.array_equal(got, golden_frames["tests_variant_400x800"])
     mp.free()
 
@@ -682,14 +682,24 @@ def test_config5_16384_map_column_slabs_against_the_oracle(fsb, oracle, gpu_ctx)
     mp.free()
 
 
-@pytest.mark.parametrize("max_cols", ["0", "100000000"], ids=["one_warp_per_column", "four_warps_per_column"])
-def test_single_frame_march_variants(fsb, oracle, gpu_ctx, fbm1024, monkeypatch, max_cols):
-    """Single frames on the texture path march with four warps per column (fsb_march_frame.cu) below a size threshold
-    and with one warp per column (fsb_march_kernel) above it; FSB_FRAME_MAX_COLS moves the threshold.  Both against the
-    oracle: filters, sentinels, smoothing, full evaluation, ragged and degenerate sizes, short and long series, a batch."""
+@pytest.mark.parametrize("variant", ["one_warp_per_column", "four_warps_per_column", "split32", "split64", "split_default"])
+def test_single_frame_march_variants(fsb, oracle, gpu_ctx, fbm1024, monkeypatch, variant):
+    """Single frames and small batches on the texture path: the depth-parallel cluster march (fsb_march_split.cu, the
+    default; 32 or 64 depth segments per group of 32 columns, FSB_SPLIT_WARPS), and behind FSB_SPLIT=0 the marches it
+    replaced -- four warps per column (fsb_march_frame.cu) below a size threshold, one warp per column (fsb_march_kernel)
+    above it; FSB_FRAME_MAX_COLS moves the threshold.  All against the oracle: filters, sentinels, smoothing, full
+    evaluation, ragged and degenerate sizes, short and long series (the longest falls back from the split march), batches."""
     col, hgt = fbm1024
     mp = gpu_ctx.upload_map(col, hgt)
-    monkeypatch.setenv("FSB_FRAME_MAX_COLS", max_cols)
+    if variant.startswith("split"):
+        if variant != "split_default":
+            monkeypatch.setenv("FSB_SPLIT_WARPS", variant[5:])
+        n0 = gpu_ctx.launch_count
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*POSES[0], SKY), fsb.default_params(), 300, 417)
+        assert gpu_ctx.launch_count - n0 == 3      # march, colour, expand: no set-up launch
+    else:
+        monkeypatch.setenv("FSB_SPLIT", "0")
+        monkeypatch.setenv("FSB_FRAME_MAX_COLS", "0" if variant == "one_warp_per_column" else "100000000")
     for filt in (1, 0):
         for sentinel in (0, 1):
             for flags in (0, fsb.FLAG_NO_CULL):
@@ -702,14 +712,62 @@ def test_single_frame_march_variants(fsb, oracle, gpu_ctx, fbm1024, monkeypatch,
     cam = fsb.Camera(512.37, 512.73, 180, 2.2, 40, 300, 1.2, SKY)
     for h, w in ((1, 1), (7, 5), (33, 9), (257, 8)):
         check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, h, w)
-    for dist in (0.0004, 0.001, 0.6, 2.0, 5.0, 30.0, 60000.0):   # n_z = 0, 1, 35, 63, 100, 245, 10954
+    for dist in (0.0004, 0.001, 0.6, 2.0, 5.0, 30.0, 2000.0, 7000.0, 60000.0):   # n_z = 0, 1, 35, 63, 100, 245, 2000, 3742, 10954
         cam.distance = dist
         check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, 64, 48)
-    cam = fsb.Camera(512.37, 512.73, 400, 2.2, 20, 900, 1.2, SKY)   # camera above the terrain: the skipped prefix
-    check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, 200, 333)
-    cams = camera_path(fsb, 1024, 3, 700)
-    frames = gpu_ctx.render_batch(cams, prm, mp, 135, 240)
-    for c, got in zip(cams, frames):
-        assert np.array_equal(got, oracle.render(ocam(oracle, c), oprm(oracle, prm), col, hgt & 0xFF, 135, 240))
+    for cam_h in (400, 700, 5000):                                  # camera above the terrain: the skipped prefix
+        cam = fsb.Camera(512.37, 512.73, cam_h, 2.2, 20, 900, 1.2, SKY)
+        check(fsb, oracle, gpu_ctx, mp, col, hgt, cam, prm, 200, 333)
+    for n, dist in ((3, 700), (7, 1500)):                           # small batches, ragged series
+        cams = camera_path(fsb, 1024, n, dist)
+        cams[n // 2].distance = 90
+        frames = gpu_ctx.render_batch(cams, prm, mp, 135, 240)
+        for c, got in zip(cams, frames):
+            assert np.array_equal(got, oracle.render(ocam(oracle, c), oprm(oracle, prm), col, hgt & 0xFF, 135, 240))
+    check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(512.37, 512.73, 150, 2.2, 9000, 700, 1.2, SKY), fsb.default_params(), 32768, 40)
     check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(512, 800, 78, 0, 100, 800, 1, SKY), fsb.tests_variant_params(), 400, 800)
     mp.free()
+
+
+def test_local_occlusion_bound_changes_no_pixel(fsb, oracle, gpu_ctx, monkeypatch):
+    """The column-parallel march skips a chunk of 32 depth steps x 32 columns when the pyramid of local height maxima
+    (built at map upload for power-of-two packed maps) proves that no sample of it can pass `occlude`.  Frames must be
+    those of the oracle with and without it (FSB_LOCAL_CULL=0), on rugged and flat terrain, both filters, both
+    sentinels, map sizes down to one pyramid level, cameras above / below / inside the terrain and far outside the map;
+    the counter of evaluated chunks must drop."""
+    monkeypatch.setenv("FSB_COLS_MIN_WARPS", "0")          # the column-parallel march also for single frames
+    rng = np.random.default_rng(11)
+    col, hgt = fsb.terrain_fbm(1024)
+    maps = [(col, hgt)]
+    yy, xx = np.mgrid[0:64, 0:256]
+    maps.append((rng.integers(0, 1 << 24, size=(64, 256), dtype=np.uint64).astype(np.uint32) | 0xFF000000,
+                 (128 + 120 * np.sin(xx / 9.0) * np.cos(yy / 5.0)).astype(np.int32)))      # non-square, steep
+    maps.append((rng.integers(0, 1 << 24, size=(2, 4), dtype=np.uint64).astype(np.uint32) | 0xFF000000,
+                 np.array([[0, 255, 3, 9], [200, 1, 77, 30]], np.int32)))                   # one pyramid level
+    spikes = np.zeros((512, 512), np.int32)
+    spikes[rng.integers(0, 512, 300), rng.integers(0, 512, 300)] = 255                        # isolated one-texel spikes
+    maps.append((rng.integers(0, 1 << 24, size=(512, 512), dtype=np.uint64).astype(np.uint32) | 0xFF000000, spikes))
+    gpu_ctx.set_profiling(True)
+    saved = []
+    for color, height in maps:
+        mp = gpu_ctx.upload_map(color, height)
+        q, r = height.shape
+        for filt in (1, 0):
+            for sentinel in (0, 1):
+                prm = fsb.default_params(filter=filt, sentinel=sentinel)
+                for (x, y, ch, ang, hor, dist, fov) in POSES[:6] + [(r / 2 + 0.3, q / 2 + 0.6, 20, 5.1, 150, 1500, 1.2),
+                                                                    (r / 3 + 0.3, q / 3 + 0.6, 300, 0.4, 60, 2500, 0.7)]:
+                    cam = fsb.Camera(x, y, ch, ang, hor, dist, fov, SKY)
+                    gpu_ctx.get_counters()
+                    a = check(fsb, oracle, gpu_ctx, mp, color, height, cam, prm, 200, 333)
+                    with_cull = gpu_ctx.get_counters()[0]
+                    monkeypatch.setenv("FSB_LOCAL_CULL", "0")
+                    b = gpu_ctx.render(cam, prm, mp, 200, 333)
+                    monkeypatch.delenv("FSB_LOCAL_CULL")
+                    without = gpu_ctx.get_counters()[0]
+                    assert np.array_equal(a, b)
+                    assert with_cull <= without
+                    saved.append((with_cull, without))
+        mp.free()
+    gpu_ctx.set_profiling(False)
+    assert sum(a for a, _ in saved) < 0.8 * sum(b for _, b in saved)
