@@ -326,6 +326,18 @@ static uint8_t *build_height_pyramid(const int32_t *hm, int q, int r, int *level
   return out;
 }
 
+/* test hook (tests/test_local_bound_cpu.py; declared in fsb_internal.h only): the pyramid as uploaded */
+int fsb_debug_height_pyramid(const int32_t *hm, int q, int r, uint8_t *out, size_t cap) {
+  int levels = 0;
+  size_t bytes = 0;
+  if (!hm || q <= 0 || r <= 0 || (q & (q - 1)) || (r & (r - 1))) return -1;
+  uint8_t *p = build_height_pyramid(hm, q, r, &levels, &bytes);
+  if (!p) return 0;
+  if (out && bytes <= cap) memcpy(out, p, bytes);
+  free(p);
+  return levels;
+}
+
 int fsb_map_new(fsb_context *ctx, const uint32_t *color, const int32_t *height, int q, int r, int mask_heights,
                 fsb_map **out) {
   if (!ctx) return FSB_ERR_ARG;
@@ -786,9 +798,11 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (env && atoi(env) >= 0) min_warps = atoi(env);
     if (warps < min_warps) pl.cols = 0;
   }
-  const char *env_split = getenv("FSB_SPLIT"); /* A/B and tests: FSB_SPLIT=0 keeps the marches of fsb_march_frame.cu / fsb_kernels.cu */
+  /* FSB_SPLIT=1 (A/B, tests): measured slower than the marches below as three launches (profiles/r2_split_march_v1.jsonl:
+   * 37.9 against 29.5 us at 1080p -- the colour pass as a launch of its own costs what the split saves) */
+  const char *env_split = getenv("FSB_SPLIT");
   if (!pl.cols && pl.mem == FSB_MEM_TEX && max_nz <= FSB_COLS_MAX_NZ && !(prm->flags & FSB_FLAG_MARCH_Z) && !ctx->force_march_z &&
-      !(env_split && atoi(env_split) == 0)) {
+      env_split && atoi(env_split) != 0) {
     /* Too few groups of 32 columns to fill the device with one warp each (single frames, small batches): the depth series
      * of every group is split over the 32 or 64 warps of a thread-block cluster (fsb_march_split.cu), 64 while the whole
      * launch still fits the device at 32 warps per SM. */

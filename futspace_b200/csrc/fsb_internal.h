@@ -108,6 +108,9 @@ int fsb_launch_l2_stream(const uint32_t *buf, size_t n_words, uint32_t *sink, in
 int fsb_launch_l2_gather(const uint32_t *buf, size_t n_sectors, uint32_t *sink, int blocks, int per_thread,
                          void *stream);
 
+/* test hook: the pyramid of local height maxima fsb_map_new uploads (fsb_api.c build_height_pyramid); -> levels */
+int fsb_debug_height_pyramid(const int32_t *hm, int q, int r, uint8_t *out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,7 +132,7 @@ __device__ __forceinline__ void load_inv_z(const float *p, float (&iz)[U]) {
  * the CTA (4 warps = 128 adjacent columns of one pose) stages them in shared memory with cp.async, two
  * chunks ahead of the one being marched: the per-step operands are LDS broadcasts (29 cycles) instead of global loads
  * queued behind the texture gathers in the same L1 pipe (round-2 ncu: the largest stall site of the first version). */
-template <bool BIL, int U, int MINB, bool XPF>
+template <bool BIL, int U, int MINB, bool LC>
 __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(const fsb_render_args a) {
   static_assert(32 % (2 * U) == 0, "a pair of register sets must tile a 32-step chunk");
   __shared__ __align__(16) float sm[3][FSB_TAB_BLOCK];
@@ -193,9 +193,10 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
     cp_async_wait_all();
     __syncthreads();
     col_step<BIL> sa[U], sb[U];
-    /* sa holds the gathers of the head of the chunk about to be marched (issued at the tail of the chunk before it) */
+    /* have_sa: sa holds the gathers of the head of the chunk about to be marched (issued at the tail of the chunk before it) */
     bool have_sa = false;
-    const bool local_cull = a.hpyr != nullptr && cull_d > -INFINITY && cull_d < INFINITY && !a.full_eval;
+    /* LC: the launch has the pyramid of local height maxima (a.hpyr); the bound needs what the map-wide one needs */
+    const bool local_cull = LC && cull_d > -INFINITY && cull_d < INFINITY && !a.full_eval;
     const float fj0 = (float)(a.col_begin + group * 32);
     int slot = 0;
     for (int c = c_first; c < c_end; ++c) {
@@ -218,11 +219,10 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
           for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, tl[u], fj);
         }
       }
-      have_sa = false;
+      have_sa = !LC;
       if (eval) {
         ++c_done;
         const float4 *tl_next = reinterpret_cast<const float4 *>(sm[slot1]);
-        const float *tz_next = sm[slot1] + 128;
         const uint32_t kw = (uint32_t)(c << 5) << FSB_ROW_BITS;
 #pragma unroll
         for (int i = 0; i < 32; i += 2 * U) {
@@ -234,15 +234,13 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
 #pragma unroll
           for (int u = 0; u < U; ++u)
             cstep_resolve<BIL>(sa[u], iza[u], cam_h, horizon, kw + ((uint32_t)(i + u) << FSB_ROW_BITS), st);
-          /* next set: the following steps of this chunk, or the head of the next one unless the local bound hides it
-           * (tested with the y-buffers as they are now; they only fall) */
-          if (i + 2 * U < 32) {
+          /* next set: the following steps of this chunk; without the local bound also the head of the next chunk (a
+           * repeated last sample in the padding projects to the same row and `occlude` keeps the earlier one).  With it,
+           * the next chunk is tested first, at the top of its turn, with nothing in flight (measured: testing here, with
+           * a register set live, spills and is 8 % slower, profiles/r2_local_cull_ab.jsonl) */
+          if (i + 2 * U < 32 || !LC) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, tl[i + 2 * U + u], fj);
-          } else if (XPF && c + 1 < c_end && !(local_cull && chunk_hidden(a, tl_next, tz_next, fj0, lane, cam_h, horizon, st.ybuf_f))) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, tl_next[u], fj);
-            have_sa = true;
+            for (int u = 0; u < U; ++u) cstep_issue<BIL>(sa[u], a, i + 2 * U < 32 ? tl[i + 2 * U + u] : tl_next[u], fj);
           }
 #pragma unroll
           for (int u = 0; u < U; ++u)
@@ -411,11 +409,12 @@ __global__ void __launch_bounds__(128) fsb_colour_kernel(const fsb_render_args a
 }
 
 /* ------------------------------------------------------------------------------------------ */
-template <bool BIL, int U, int MINB, bool XPF = true>
+template <bool BIL, int U, int MINB>
 static int launch_marchc_t(const fsb_render_args &a, cudaStream_t s) {
   const int ncols = a.col_end - a.col_begin;
   dim3 grid((ncols + FSB_MC_WARPS * 32 - 1) / (FSB_MC_WARPS * 32), a.n_poses);
-  fsb_marchc_kernel<BIL, U, MINB, XPF><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
+  if (a.hpyr) fsb_marchc_kernel<BIL, U, MINB, true><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
+  else fsb_marchc_kernel<BIL, U, MINB, false><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -433,7 +432,6 @@ extern "C" int fsb_launch_march_cols(const fsb_render_args *a, void *stream, int
   else if (bil && variant == 2) rc = launch_marchc_t<true, 2, 8>(*a, s);
   else if (bil && variant == 3) rc = launch_marchc_t<true, 2, 10>(*a, s);
   else if (bil && variant == 4) rc = launch_marchc_t<true, 8, 4>(*a, s);
-  else if (bil && variant == 5) rc = launch_marchc_t<true, 4, 6, false>(*a, s);
   else
     rc = bil ? launch_marchc_t<true, 4, 6>(*a, s) : launch_marchc_t<false, 4, 6>(*a, s);
   if (launches) ++*launches;
