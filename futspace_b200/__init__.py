@@ -71,6 +71,7 @@ SYMBOLS = {
     "fsb_context_set_profiling": (_ci, [_vp, _ci]),
     "fsb_context_get_profile": (_ci, [_vp, _P(ctypes.c_double), _P(ctypes.c_int64)]),
     "fsb_context_get_counters": (_ci, [_vp, _P(ctypes.c_uint64), _P(ctypes.c_uint64)]),
+    "fsb_context_paint_trips": (ctypes.c_uint64, [_vp]),
     "fsb_params_default": (None, [_P(Params)]),
     "fsb_params_tests_variant": (None, [_P(Params)]),
     "fsb_get_zs": (_ci, [_cf, _cf, _cf, _vp, _ci]),
@@ -237,6 +238,11 @@ class Context:
         a, b = ctypes.c_uint64(), ctypes.c_uint64()
         self._check(lib().fsb_context_get_counters(self.handle, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
+
+    @property
+    def paint_trips(self):
+        """warp-wide colour trips of the paint kernel in the interval the last get_counters() closed"""
+        return int(lib().fsb_context_paint_trips(self.handle))
 
     def upload_map(self, color, height, mask_heights=True):
         color = np.ascontiguousarray(color, dtype=np.uint32)

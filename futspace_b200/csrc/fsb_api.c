@@ -54,6 +54,7 @@ struct fsb_context {
   const float *lut;               /* device address of the colour look-up table */
   int force_march_z;              /* env FSB_MARCH_Z: always the lanes-over-depth march */
   int no_pdl;                     /* env FSB_PDL=0: no programmatic dependent launch for single frames */
+  uint64_t paint_trips;           /* colour trips of the paint kernel seen by the last fsb_context_get_counters */
   char name[128];
 };
 
@@ -627,6 +628,8 @@ typedef struct {
   int rec4;       /* 4-byte records */
   int cand_cap;   /* candidate words per column */
   int slice_len;  /* colour pass: records per warp (0: whole lists) */
+  int paint;      /* colour pass and expand as one kernel (fsb_paint.cu) */
+  int seg_bands;  /* paint: bands of 32 rows per warp (0: whole columns) */
   int ncols_pad;
 } render_plan;
 
@@ -691,8 +694,8 @@ int fsb_context_set_profiling(fsb_context *ctx, int enable) {
   if (enable && !ctx->pev[0])
     for (int i = 0; i < 5; ++i) CU(ctx, cudaEventCreate(&ctx->pev[i]));
   if (enable && !ctx->stats_dev) {
-    CU(ctx, cudaMalloc((void **)&ctx->stats_dev, 16));
-    CU(ctx, cudaMemsetAsync(ctx->stats_dev, 0, 16, ctx->stream));
+    CU(ctx, cudaMalloc((void **)&ctx->stats_dev, 32));
+    CU(ctx, cudaMemsetAsync(ctx->stats_dev, 0, 32, ctx->stream));
   }
   int rc = prof_collect(ctx);
   ctx->profiling = enable != 0;
@@ -702,15 +705,18 @@ int fsb_context_set_profiling(fsb_context *ctx, int enable) {
 int fsb_context_get_counters(fsb_context *ctx, uint64_t *chunks_evaluated, uint64_t *records) {
   if (!ctx || !chunks_evaluated || !records) return FSB_ERR_ARG;
   if (!ctx->stats_dev) return set_err(ctx, FSB_ERR_ARG, "fsb_context_get_counters: profiling was never enabled");
-  unsigned long long h[2] = {0, 0};
+  unsigned long long h[4] = {0, 0, 0, 0};
   CU(ctx, cudaSetDevice(ctx->device));
-  CU(ctx, cudaMemcpyAsync(h, ctx->stats_dev, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaMemsetAsync(ctx->stats_dev, 0, 16, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(h, ctx->stats_dev, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemsetAsync(ctx->stats_dev, 0, 32, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   *chunks_evaluated = h[0];
   *records = h[1];
+  ctx->paint_trips = h[2];
   return FSB_OK;
 }
+
+uint64_t fsb_context_paint_trips(const fsb_context *ctx) { return ctx ? ctx->paint_trips : 0; }
 
 int fsb_context_get_profile(fsb_context *ctx, double *ms, int64_t *launches) {
   if (!ctx || !ms || !launches) return FSB_ERR_ARG;
@@ -837,6 +843,17 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (pl.split) pl.slice_len = 8; /* a lone frame has 60 lists of 32 columns: short slices spread the filter over the device */
     const char *env = getenv("FSB_COLOUR_SLICE");
     if (env && atoi(env) >= 0) pl.slice_len = atoi(env);
+    /* 4-byte record case: colour pass and expand run as one kernel, the records stay in shared memory (fsb_paint.cu);
+     * FSB_PAINT=0 (A/B) keeps the two launches */
+    env = getenv("FSB_PAINT");
+    pl.paint = pl.rec4 && !pl.split && !(env && atoi(env) == 0);
+    if (pl.paint) {
+      const int n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
+      /* whole columns per warp when there are plenty of lists, otherwise segments of bands */
+      pl.seg_bands = pl.slice_len == 0 ? 0 : pl.slice_len == 64 ? (n_bands + 1) / 2 : (n_bands + 3) / 4;
+      env = getenv("FSB_PAINT_SEG"); /* tuning aid: bands per paint warp */
+      if (env && atoi(env) >= 0) pl.seg_bands = atoi(env);
+    }
   }
   if ((rc = ensure_scratch(ctx, sc, n, ncols, h, &pl))) return rc;
   if (n > 1) {
@@ -915,14 +932,15 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     else
       CU(ctx, (cudaError_t)fsb_launch_march_cols(&a, ctx->stream, &ctx->launches));
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
-    CU(ctx, (cudaError_t)fsb_launch_colour(&a, pl.slice_len, ctx->stream, &ctx->launches));
+    if (!pl.paint) CU(ctx, (cudaError_t)fsb_launch_colour(&a, pl.slice_len, ctx->stream, &ctx->launches));
   } else {
     if (pl.frame) CU(ctx, (cudaError_t)fsb_launch_march_frame(&a, ctx->stream, &ctx->launches));
     else CU(ctx, (cudaError_t)fsb_launch_march(&a, pl.mem, ctx->stream, &ctx->launches));
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
   }
   if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[3], ctx->stream));
-  CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));
+  if (pl.paint) CU(ctx, (cudaError_t)fsb_launch_paint(&a, pl.seg_bands, ctx->stream, &ctx->launches));
+  else CU(ctx, (cudaError_t)fsb_launch_expand(&a, ctx->stream, &ctx->launches));
   if (ctx->profiling) {
     CU(ctx, cudaEventRecord(ctx->pev[4], ctx->stream));
     ctx->prof_pending = 1;

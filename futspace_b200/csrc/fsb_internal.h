@@ -98,6 +98,9 @@ int fsb_launch_march_split(const fsb_render_args *a, const fsb_frame_consts *sin
 int fsb_launch_march_cols(const fsb_render_args *a, void *stream, int64_t *launches);
 /* colour pass: candidate lists -> the records fsb_launch_expand consumes; slice_len: records per warp (0: whole lists) */
 int fsb_launch_colour(const fsb_render_args *a, int slice_len, void *stream, int64_t *launches);
+/* colour pass + expand as one kernel (fsb_paint.cu): 4-byte record case of the column-parallel path; seg_bands: bands of 32 rows
+ * per warp (0: the whole column) */
+int fsb_launch_paint(const fsb_render_args *a, int seg_bands, void *stream, int64_t *launches);
 const float *fsb_lut_device_address(void); /* after fsb_launch_lut_init */
 int fsb_launch_lut_init(void *stream); /* fills the colour look-up table of the march (once per device, before any render) */
 int fsb_launch_shadow(const uint32_t *color, const int32_t *height, int q, int r, const float *sun, int out_q, int out_r,

@@ -560,18 +560,26 @@ def test_one_pixel_wide_frame_with_horizon_below_the_frame(fsb, oracle, gpu_ctx,
     mp.free()
 
 
-@pytest.mark.parametrize("slice_len", [0, 1, 7, 32])
-def test_column_parallel_march_on_single_frames_and_colour_slices(fsb, oracle, gpu_ctx, fbm1024, monkeypatch, slice_len):
-    """The column-parallel march + colour pass is the batch path; FSB_COLS_MIN_WARPS=0 forces it for single frames and
-    FSB_COLOUR_SLICE cuts the colour pass into slices of the record lists.  Same frames as the oracle whatever the path:
-    both filters, both sentinels, smoothing, ragged widths, ragged series in a batch, empty and one-sample series."""
+@pytest.mark.parametrize("slice_len,paint_seg", [(0, None), (1, None), (7, None), (32, None), (0, 0), (0, 1), (0, 3), (32, -1)],
+                         ids=["slice0", "slice1", "slice7", "slice32", "paint_columns", "paint_seg1", "paint_seg3", "paint_default"])
+def test_column_parallel_march_on_single_frames_and_colour_slices(fsb, oracle, gpu_ctx, fbm1024, monkeypatch, slice_len,
+                                                                  paint_seg):
+    """The column-parallel march is the batch path, followed either by the colour pass and expand as two launches
+    (FSB_PAINT=0; FSB_COLOUR_SLICE cuts the colour pass into slices of the record lists) or by the paint kernel that does both
+    (the default; FSB_PAINT_SEG = bands of 32 rows per warp, 0 = whole columns).  FSB_COLS_MIN_WARPS=0 forces the path for
+    single frames.  Same frames as the oracle whatever the path: both filters, both sentinels, smoothing, ragged widths,
+    ragged series in a batch, empty and one-sample series."""
     col, hgt = fbm1024
     mp = gpu_ctx.upload_map(col, hgt)
     monkeypatch.setenv("FSB_COLS_MIN_WARPS", "0")              # read per call (fsb_api.c)
     monkeypatch.setenv("FSB_COLOUR_SLICE", str(slice_len))
+    if paint_seg is None:
+        monkeypatch.setenv("FSB_PAINT", "0")
+    elif paint_seg >= 0:
+        monkeypatch.setenv("FSB_PAINT_SEG", str(paint_seg))
     n0 = gpu_ctx.launch_count
     check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*POSES[0], SKY), fsb.default_params(), 300, 417)
-    assert gpu_ctx.launch_count - n0 == 4                      # set-up, march, colour, expand
+    assert gpu_ctx.launch_count - n0 == (4 if paint_seg is None else 3)   # set-up, march, colour + expand | paint
     for filt in (1, 0):
         for sentinel in (0, 1):
             prm = fsb.default_params(filter=filt, sentinel=sentinel)
@@ -611,22 +619,27 @@ def test_smoothing_at_the_maximum_frame_height(fsb, oracle, gpu_ctx, fbm1024, mo
     mp.free()
 
 
-def test_batch_paths_agree(fsb, oracle, gpu_ctx, fbm1024):
-    """A batch large enough for the column-parallel march by default (80 poses x 60 groups of 32 columns) against the
-    lanes-over-depth march (FSB_FLAG_MARCH_Z) and the oracle, frame by frame; launch counts tell the two paths apart."""
+def test_batch_paths_agree(fsb, oracle, gpu_ctx, fbm1024, monkeypatch):
+    """A batch large enough for the column-parallel march by default (80 poses x 60 groups of 32 columns): march + paint
+    (the default), march + colour pass + expand (FSB_PAINT=0), the lanes-over-depth march (FSB_FLAG_MARCH_Z) and the oracle,
+    frame by frame; launch counts tell the paths apart."""
     col, hgt = fbm1024
     mp = gpu_ctx.upload_map(col, hgt)
     cams = camera_path(fsb, 1024, 80, 900)
     for c in cams:
         c.horizon = 40
     h, w = 96, 1920
+    p0 = gpu_ctx.launch_count
+    c = gpu_ctx.render_batch(cams, fsb.default_params(), mp, h, w)
+    monkeypatch.setenv("FSB_PAINT", "0")                       # read per call (fsb_api.c)
     n0 = gpu_ctx.launch_count
     a = gpu_ctx.render_batch(cams, fsb.default_params(), mp, h, w)
     n1 = gpu_ctx.launch_count
     b = gpu_ctx.render_batch(cams, fsb.default_params(flags=fsb.FLAG_MARCH_Z), mp, h, w)
     n2 = gpu_ctx.launch_count
     assert (n1 - n0) % 4 == 0 and (n2 - n1) % 3 == 0 and (n1 - n0) // 4 == (n2 - n1) // 3   # + the colour pass
-    assert np.array_equal(a, b)
+    assert n0 - p0 == n2 - n1                                  # set-up, march, paint
+    assert np.array_equal(a, b) and np.array_equal(a, c)
     for i in (0, 31, 32, 63, 79):
         want = oracle.render(ocam(oracle, cams[i]), oprm(oracle, fsb.default_params()), col, hgt & 0xFF, h, w)
         assert np.array_equal(a[i], want), i
