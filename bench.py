@@ -366,14 +366,18 @@ def measure(torch, F, O, ctx, st, flush, wl, wl_key, m, col, hgt, mp, P, steps, 
     kern_cull = {k: v[0] / 2 for k, v in prof_cull.items()}
     kern_full = {k: v[0] / 2 for k, v in prof_full.items()}
     kernels = {}
-    for name in ("march", "colour", "expand"):
-        e = {"ms_per_step": kern_cull[name], "ms_per_step_full_evaluation": kern_full[name]}
-        if rates and name in rates and kern_cull[name] > 1e-4:
+    # the batch path paints (colour pass + expand as one kernel, fsb_paint.cu): the library's "colour" interval is then empty and
+    # its "expand" interval is the paint kernel
+    painted = kern_cull["colour"] < 0.05 * kern_cull["expand"]
+    names = {"march": "march", "paint": "expand"} if painted else {"march": "march", "colour": "colour", "expand": "expand"}
+    for name, slot in names.items():
+        e = {"ms_per_step": kern_cull[slot], "ms_per_step_full_evaluation": kern_full[slot]}
+        if rates and name in rates and kern_cull[slot] > 1e-4:
             r = rates[name]
             e["warp_instructions_per_pose_ncu"] = r["inst_per_pose"]
             # march instructions scale with the chunks evaluated, the others do not depend on the bound
             scale = (chunks_cull / max(chunks_full, 1.0)) / r.get("chunks_frac_in_capture", 1.0) if name == "march" else 1.0
-            e["issue_slot_frac"] = r["inst_per_pose"] * scale * P / (slots_per_ms * kern_cull[name])
+            e["issue_slot_frac"] = r["inst_per_pose"] * scale * P / (slots_per_ms * kern_cull[slot])
             e["dram_bytes_per_pose_ncu"] = r["dram_bytes_per_pose"]
             if name == "march":
                 e["l2_sectors_per_sample_ncu"] = r["lts_tex_read_sectors_per_pose"] / (32.0 * chunks_cull / P)
@@ -383,11 +387,17 @@ def measure(torch, F, O, ctx, st, flush, wl, wl_key, m, col, hgt, mp, P, steps, 
     kernels["march"]["tex_pipe_frac"] = chunks_cull * TLD4_CYCLES_PER_SM / (SM_COUNT * f_sm * 1e3 * kern_cull["march"])
     kernels["march"]["tex_pipe_frac_full_evaluation"] = (chunks_full * TLD4_CYCLES_PER_SM /
                                                          (SM_COUNT * f_sm * 1e3 * kern_full["march"]))
-    # expand: HBM bound -- the frame must be written once
-    kernels["expand"]["hbm_frac_frame_bytes_only"] = frame_alg * P / (kern_cull["expand"] * 1e-3) / 1e9 / peak
-    if rates and "expand" in rates:
-        kernels["expand"]["hbm_frac_ncu_traffic"] = (rates["expand"]["dram_bytes_per_pose"] * P /
-                                                     (kern_cull["expand"] * 1e-3) / 1e9 / peak)
+    # the kernel that writes the frame (paint, or expand): HBM floor -- the frame must be written once
+    writer = "paint" if painted else "expand"
+    kernels[writer]["hbm_frac_frame_bytes_only"] = frame_alg * P / (kern_cull["expand"] * 1e-3) / 1e9 / peak
+    if rates and writer in rates:
+        kernels[writer]["hbm_frac_ncu_traffic"] = (rates[writer]["dram_bytes_per_pose"] * P /
+                                                   (kern_cull["expand"] * 1e-3) / 1e9 / peak)
+    if painted:
+        kernels["paint"]["records_per_frame"] = records / P
+        if ctx.paint_trips:
+            # lanes of a colour trip that filter a record (the rest wait: their ring is full or their list is behind)
+            kernels["paint"]["colour_lane_utilisation"] = records * 2.0 / (32.0 * ctx.paint_trips)
     tr = rates["march"]["dram_bytes_per_pose"] * poses_per_launch if rates and "march" in rates else None
     share = march_ms / sum(v[0] for v in prof_full.values())
     roofline = {"bound": "hbm", "kernel": "fsb_marchc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -399,7 +409,9 @@ def measure(torch, F, O, ctx, st, flush, wl, wl_key, m, col, hgt, mp, P, steps, 
                 "note": "HBM is the bound the contract names, not the limiter: the 16 B per depth sample of SURVEY 8d are "
                         "served by the texture unit from L1/L2 (traffic = what ncu saw cross DRAM).  What binds the march "
                         "is the texture pipe (one tld4 per 32 samples at 8.2 cycles per SM: kernels.march.tex_pipe_frac) and "
-                        "instruction issue (kernels.march.issue_slot_frac); the frame store binds expand (hbm_frac_*).",
+                        "instruction issue (kernels.march.issue_slot_frac); the kernel that writes the frame (paint: colour pass + "
+                        "expand as one kernel) is bound by instruction issue with the HBM floor of the frame bytes beside it "
+                        "(kernels.paint.issue_slot_frac, hbm_frac_*).",
                 "default_path": {"march_launch_ms": prof_cull["march"][0] / prof_cull["march"][1],
                                  "chunks_evaluated_of_all": chunks_cull / all_chunks,
                                  "records_per_frame": records / P}}

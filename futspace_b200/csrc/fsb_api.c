@@ -606,6 +606,7 @@ static int ensure_tables(fsb_context *ctx, fsb_scratch *sc, int n_poses, int tab
 #define FSB_RB_SHIFT 5                   /* band of the per-column record index = 32 rows (fsb_expand_kernel) */
 #define FSB_MAX_H 32768
 #define FSB_SCRATCH_BUDGET ((size_t)8192 << 20)
+#define FSB_CAND_PAD 1024                /* words in front of the candidate lists (the paint kernel's prefetch reaches below a list's start) */
 #define FSB_COLS_MAX_NZ (1 << 17)        /* candidate word of the column-parallel march: row (15 bits) | sample index (17 bits) */
 
 static int grow(fsb_context *ctx, void **ptr, size_t *cap, size_t need) {
@@ -642,7 +643,8 @@ static int ensure_scratch(fsb_context *ctx, fsb_scratch *sc, int n_poses, int nc
   if ((rc = grow(ctx, (void **)&sc->sidx, &sc->sidx_cap, np * lc * (n_bands + 1) * 4))) return rc;
   if (pl->cols) {
     const size_t lists = np * pl->ncols_pad;
-    if ((rc = grow(ctx, (void **)&sc->cand, &sc->cand_cap, lists * pl->cand_cap * 4))) return rc;
+    /* + a pad in front: the paint kernel prefetches a few entries past the start of a list (fsb_paint.cu) */
+    if ((rc = grow(ctx, (void **)&sc->cand, &sc->cand_cap, lists * pl->cand_cap * 4 + FSB_CAND_PAD * 4))) return rc;
     if ((rc = grow(ctx, (void **)&sc->cand_cnt, &sc->cand_cnt_cap, lists * 4))) return rc;
   }
   return FSB_OK;
@@ -921,7 +923,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
       a.pyr_levels = map->pyr_levels;
     }
   }
-  a.cand = sc->cand;
+  a.cand = sc->cand ? sc->cand + FSB_CAND_PAD : NULL;
   a.cand_cnt = sc->cand_cnt;
   a.cand_cap = pl.cand_cap;
   a.ncols_pad = pl.ncols_pad;

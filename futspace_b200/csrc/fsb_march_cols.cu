@@ -133,10 +133,13 @@ __device__ __forceinline__ void load_inv_z(const float *p, float (&iz)[U]) {
  * the CTA (4 warps = 128 adjacent columns of one pose) stages them in shared memory with cp.async, two
  * chunks ahead of the one being marched: the per-step operands are LDS broadcasts (29 cycles) instead of global loads
  * queued behind the texture gathers in the same L1 pipe (round-2 ncu: the largest stall site of the first version). */
-template <bool BIL, int U, int MINB, bool LC>
+template <bool BIL, int U, int MINB, bool LC, bool PW>
 __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(const fsb_render_args a) {
   static_assert(32 % (2 * U) == 0, "a pair of register sets must tile a 32-step chunk");
-  __shared__ __align__(16) float sm[3][FSB_TAB_BLOCK];
+  /* PW: every warp stages the table chunks for itself (no CTA barrier: with the local occlusion bound the four groups of a
+   * CTA skip different chunks, and the ones that skip would wait at the barrier for the one that marches) */
+  __shared__ __align__(16) float sm_all[PW ? FSB_MC_WARPS : 1][3][FSB_TAB_BLOCK];
+  float (*sm)[FSB_TAB_BLOCK] = sm_all[PW ? (threadIdx.x >> 5) : 0];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pose = blockIdx.y;
   const int ncols = a.col_end - a.col_begin;
@@ -182,17 +185,26 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
   if (c_first < c_end) {
     /* staging: threads 0..31 copy one {sx,sy,dx,dy} each, threads 32..39 four inv_z each; chunks c_first and c_first + 1
      * first (the table is padded with entries that repeat the last sample) */
-    const bool stager = tid < FSB_TAB_BLOCK / 4;
-    const char *gsrc = tid < 32 ? reinterpret_cast<const char *>(line + c_first * 32 + tid)
-                                : reinterpret_cast<const char *>(invz + c_first * 32 + (tid - 32) * 4);
-    const int gstep = tid < 32 ? 32 * 16 : 32 * 4; /* bytes per chunk in the source array */
+    const bool stager = PW ? true : tid < FSB_TAB_BLOCK / 4;
+    const char *gsrc = (PW || tid < 32) ? reinterpret_cast<const char *>(line + c_first * 32 + (PW ? lane : tid))
+                                        : reinterpret_cast<const char *>(invz + c_first * 32 + (tid - 32) * 4);
+    const int gstep = (PW || tid < 32) ? 32 * 16 : 32 * 4; /* bytes per chunk in the source array */
+    /* PW: lanes 0..7 copy the chunk's 32 inv_z as well */
+    const char *gsrc2 = reinterpret_cast<const char *>(invz + c_first * 32 + (lane & 7) * 4);
+    const bool stager2 = PW && lane < 8;
     if (stager) {
-      cp_async16(&sm[0][tid * 4], gsrc);
-      cp_async16(&sm[1][tid * 4], gsrc + gstep);
+      cp_async16(&sm[0][(PW ? lane : tid) * 4], gsrc);
+      cp_async16(&sm[1][(PW ? lane : tid) * 4], gsrc + gstep);
+    }
+    if (stager2) {
+      cp_async16(&sm[0][128 + lane * 4], gsrc2);
+      cp_async16(&sm[1][128 + lane * 4], gsrc2 + 128);
     }
     gsrc += 2 * gstep;
+    gsrc2 += 2 * 128;
     cp_async_wait_all();
-    __syncthreads();
+    if (PW) __syncwarp();
+    else __syncthreads();
     col_step<BIL> sa[U], sb[U];
     /* have_sa: sa holds the gathers of the head of the chunk about to be marched (issued at the tail of the chunk before it) */
     bool have_sa = false;
@@ -203,8 +215,10 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
     for (int c = c_first; c < c_end; ++c) {
       const int slot1 = slot == 2 ? 0 : slot + 1, slot2 = slot1 == 2 ? 0 : slot1 + 1;
       /* chunk c + 2 -> the slot chunk c - 1 was read from (every warp has passed the barrier that ended it) */
-      if (stager) cp_async16(&sm[slot2][tid * 4], gsrc);
+      if (stager) cp_async16(&sm[slot2][(PW ? lane : tid) * 4], gsrc);
       gsrc += gstep;
+      if (stager2) cp_async16(&sm[slot2][128 + lane * 4], gsrc2);
+      gsrc2 += 128;
       const float4 *tl = reinterpret_cast<const float4 *>(sm[slot]);
       const float *tz = sm[slot] + 128;
       if (active && !a.full_eval) {
@@ -249,7 +263,10 @@ __global__ void __launch_bounds__(FSB_MC_WARPS * 32, MINB) fsb_marchc_kernel(con
         }
       }
       cp_async_wait_all();
-      if (!__syncthreads_or(active)) break; /* chunk c + 2 visible; everyone is done with chunk c */
+      if (PW) {
+        __syncwarp();
+        if (!active) break;
+      } else if (!__syncthreads_or(active)) break; /* chunk c + 2 visible; everyone is done with chunk c */
       slot = slot1;
     }
   }
@@ -363,8 +380,14 @@ template <bool BIL, int U, int MINB>
 static int launch_marchc_t(const fsb_render_args &a, cudaStream_t s) {
   const int ncols = a.col_end - a.col_begin;
   dim3 grid((ncols + FSB_MC_WARPS * 32 - 1) / (FSB_MC_WARPS * 32), a.n_poses);
-  if (a.hpyr) fsb_marchc_kernel<BIL, U, MINB, true><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
-  else fsb_marchc_kernel<BIL, U, MINB, false><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
+  static int per_warp = -1; /* tuning aid: FSB_MARCHC_PW=0 -> the CTA stages the table chunks once for its four warps */
+  if (per_warp < 0) {
+    const char *e = getenv("FSB_MARCHC_PW");
+    per_warp = e ? atoi(e) != 0 : 1;
+  }
+  if (a.hpyr && per_warp) fsb_marchc_kernel<BIL, U, MINB, true, true><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
+  else if (a.hpyr) fsb_marchc_kernel<BIL, U, MINB, true, false><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
+  else fsb_marchc_kernel<BIL, U, MINB, false, false><<<grid, FSB_MC_WARPS * 32, 0, s>>>(a);
   return (int)cudaGetLastError();
 }
 

@@ -4,7 +4,7 @@
  *   fsb_paint_kernel   one warp per (pose, group of 32 columns[, segment of bands]), lane = column.  The warp walks its
  *                      columns' candidate lists (fsb_marchc_kernel: row | sample index << 15, rows strictly decreasing)
  *                      BACKWARD, i.e. down the screen from row 0: png_color / png_color_filtered of a candidate
- *                      (fut/render_functions.fut:91-105) goes into a per-lane ring of 32 entries in shared memory, and band
+ *                      (fut/render_functions.fut:91-105) goes into a per-lane ring of 32 colours in shared memory, and band
  *                      by band (32 rows) the ring is drained into pixels: replicate + scatter (fut/voxel_renderer.fut:244),
  *                      the fill_vline scan (:246), sky (:248) and the transpose (:251) exactly as fsb_expand4_kernel does
  *                      them -- the running colour is a register that lives across the whole column.
@@ -17,10 +17,14 @@
  * never travel through DRAM (1.0 MB written + 1.6 MB read per 1080p pose before, none now), the band index and its
  * dependent global loads are gone, and the walk reads its next record from shared memory.
  *
- * Ring entry: rgb | (row & 127) << 24 | (alpha == 0xFF) << 31 -- the 4-byte record of fsb_expand4_kernel with seven row bits:
- * a lane only colours ahead of the band being painted while the candidate's row is less than 96 rows past the band's end, so
- * the rows in a ring span fewer than 128 and the low seven bits identify one.  Only launched for the 4-byte record case
- * (packed map whose alpha byte is 0x00 or 0xFF, no smoothing); everything else keeps fsb_colour_kernel + fsb_expand*_kernel.
+ * Ring and masks: a ring entry is the finished 32-bit colour; WHERE the entries start is kept per lane as two 32-bit row
+ * masks, of the band being painted and of the next one (a lane colours ahead of the band being painted while its ring has
+ * room and the candidate lies in the next band at most).  The row loop tests one mask bit per row; an entry is popped
+ * when the bit is set.  Lanes colour ahead independently, so a trip of 32 lanes is full as long as the lists are not
+ * exhausted: 93 % of the lanes of a trip filter a record (fsb_context_paint_trips).
+ *
+ * Only launched for the 4-byte record case (packed map whose alpha byte is 0x00 or 0xFF, no smoothing); everything else keeps
+ * fsb_colour_kernel + fsb_expand*_kernel.
  *
  * Float discipline as in fsb_kernels.cu: every parity-relevant operation uses the round-to-nearest intrinsics.
  */
@@ -32,13 +36,14 @@
 #define FSB_PAINT_WARPS 4
 #define FSB_RING 32      /* entries per lane (power of two, >= 32: a band can hold one record per row) */
 #define FSB_PAINT_SMEM ((FSB_PAINT_WARPS + 1) * 4096)
+#define FSB_PAINT_PF 4   /* L2 prefetch distance of the candidate words, in trips (measured: 3-5 alike, 8+ worse) */
 #define FSB_RUNAHEAD 32  /* rows past the end of the band a lane may colour ahead: the next band (mask1) */
 
 /* seg_bands > 0: blockIdx.z selects a segment of seg_bands bands of the frame (medium batches: more, shorter warps); the
  * warp finds its first candidate by bisection of the list (rows strictly decrease along it) and colours the one record above
  * its first band a second time for the running colour that enters it.  seg_bands == 0: the whole column. */
 template <bool BIL, int V>
-__global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 4) ? ((V & 1) ? 7 : 8) : 9) fsb_paint_kernel(const fsb_render_args a, int seg_bands) {
+__global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 1) ? 9 : 8) fsb_paint_kernel(const fsb_render_args a, int seg_bands, int pf_dist) {
   __shared__ float sq_sm[256]; /* (c/255)^2: the second-stage operands of the three mixes */
   __shared__ uint32_t bias_slot;
   extern __shared__ uint32_t ring_dyn[]; /* FSB_PAINT_WARPS x 4096 bytes of rings + 4096 of alignment slack */
@@ -102,14 +107,16 @@ __global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 4) ?
 
   /* software pipeline of the colour trips: the candidate word of the trip after next and the depth-table entry of the next
    * trip are in flight while this trip's record is filtered (the table address depends on the word) */
+  /* wp = address of candidate p, stepped by -128 bytes per trip: the word loads and the L2 prefetch address it with
+   * immediate offsets.  (A fresh address register pair per load was overwritten by the next address computation a few
+   * instructions later, which had to wait until the load unit had read it -- 17 % of the stall samples, ncu r2l.) */
+  const uint32_t *wp = src + (ptrdiff_t)p * 32;
   uint32_t word_1 = 0, word_2 = 0, word_3 = 0;
   float4 l_1 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p >= 0) word_1 = src[(size_t)p * 32];
   if (p >= 1) word_2 = src[(size_t)(p - 1) * 32];
-  if ((V & 5) && p >= 2) word_3 = src[(size_t)(p - 2) * 32];
+  if ((V & 4) && p >= 2) word_3 = src[(size_t)(p - 2) * 32];
   if (p >= 0) l_1 = __ldg(line + (word_1 >> FSB_ROW_BITS));
-  float4 l_2 = make_float4(0.f, 0.f, 0.f, 0.f); /* V & 1: the table entry of the trip after next as well */
-  if ((V & 1) && !(V & 4) && p >= 1) l_2 = __ldg(line + (word_2 >> FSB_ROW_BITS));
   /* PIPE (bilinear): the three gathers of a record are issued one trip before its mixes run -- channel by channel into the
    * registers the record before it has just consumed -- so a trip never waits for the texture unit.  `pd` is the record
    * whose gathers are in flight (or, for the rare record that takes the general argb.mix, its finished colour). */
@@ -126,9 +133,10 @@ __global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 4) ?
       pend_prepare(a, l, fj, word_1 & FSB_ROW_MASK, nx, nxx, nyy, nu, nv);
       word_1 = word_2;
       --p;
+      wp -= 32;
       if (p >= 0) l_1 = __ldg(line + (word_1 >> FSB_ROW_BITS));
       word_2 = word_3;
-      if (p >= 2) word_3 = src[(size_t)(p - 2) * 32];
+      if (p >= 2) word_3 = wp[-64];
       pd = nx;
       if (nx.unit) {
         FSB_TLD4_F32C("b", a.tex_f, nu, nv, pd.t[0][2], pd.t[0][3], pd.t[0][1], pd.t[0][0]);
@@ -177,9 +185,11 @@ __global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 4) ?
             pend_prepare(a, l, fj, word_1 & FSB_ROW_MASK, nx, nxx, nyy, nu, nv);
             word_1 = word_2;
             --p;
+            wp -= 32;
             if (p >= 0) l_1 = __ldg(line + (word_1 >> FSB_ROW_BITS));
             word_2 = word_3;
-            if (p >= 2) word_3 = src[(size_t)(p - 2) * 32];
+            if (p >= 2) word_3 = wp[-64];
+            if (pf_dist) asm volatile("prefetch.global.L2 [%0 + %1];" ::"l"(wp), "n"(-128 * FSB_PAINT_PF));
           }
           const bool gather = nxt && nx.unit;
           uint32_t colour;
@@ -215,15 +225,25 @@ __global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 4) ?
         const float4 l = l_1;
         word_1 = word_2;
         --p;
-        if (V & 1) { /* three words and two table entries deep */
-          l_1 = l_2;
-          word_2 = word_3;
-          if (p >= 1) l_2 = __ldg(line + (word_2 >> FSB_ROW_BITS));
-          if (p >= 2) word_3 = src[(size_t)(p - 2) * 32];
-        } else {
-          if (p >= 1) word_2 = src[(size_t)(p - 1) * 32];
-          if (p >= 0) l_1 = __ldg(line + (word_1 >> FSB_ROW_BITS));
+        wp -= 32;
+        /* Loads of the next trips, in this order and as volatile asm so that the order survives: the table entry of the next
+         * record (its address comes from a word that arrived a trip ago), then the word after it, then the L2 prefetch.
+         * (With the word load first, the shift that forms the table address waited for it -- the two loads share a
+         * scoreboard -- and exposed the whole L2 latency in every trip: 17 % of the stall samples, ncu r2m.)
+         * The prefetch brings the candidate word of FSB_PAINT_PF trips ahead from DRAM to L2 (no register, no scoreboard; the
+         * lists of a large batch do not stay in L2 between the march and this kernel, and a register prefetch cannot reach
+         * further than one trip).  Unclamped: below the start of a list lies the previous group's list or the pad in front
+         * of the buffer (fsb_api.c).
+         * Measured and dropped (profiles/r2_paint_variants.txt): this record's gathers issued before these loads and the
+         * ring bookkeeping (the texture wait falls from 25 to 16 % of the stall samples, but the split form costs 24
+         * instructions more per trip: 1.64 against 1.55 ms), and the gathers issued a whole trip ahead (FSB_PAINT_VARIANT=4:
+         * no texture wait, +20 % instructions, a gain only at 4K). */
+        if (p >= 0) {
+          const float4 *tp = line + (word_1 >> FSB_ROW_BITS);
+          asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(l_1.x), "=f"(l_1.y), "=f"(l_1.z), "=f"(l_1.w) : "l"(tp));
         }
+        if (p >= 1) asm volatile("ld.global.u32 %0, [%1 + -128];" : "=r"(word_2) : "l"(wp));
+        if (pf_dist) asm volatile("prefetch.global.L2 [%0 + %1];" ::"l"(wp), "n"(-128 * FSB_PAINT_PF));
         const float x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
         const float y = __fadd_rn(l.y, __fmul_rn(fj, l.w));
         const uint32_t colour = colour_of<BIL, true>(a, x, y, un, sq, sq_sm_biased);
@@ -301,10 +321,13 @@ extern "C" int fsb_launch_paint(const fsb_render_args *a, int seg_bands, void *s
   const int groups = a->ncols_pad >> 5;
   const int segs = seg_bands > 0 ? (a->n_bands + seg_bands - 1) / seg_bands : 1;
   dim3 grid((groups + FSB_PAINT_WARPS - 1) / FSB_PAINT_WARPS, a->n_poses, segs);
-  static int variant = -1; /* tuning aid: FSB_PAINT_VARIANT, bit 0 = three-deep candidate prefetch, bit 1 = 10 CTAs per SM */
+  /* tuning aids: FSB_PAINT_VARIANT: 1 = 9 CTAs per SM (56 registers), 2 = 10 CTAs per SM (48; default: 8 CTAs, 64 registers), 4 = gathers pipelined across trips; FSB_PAINT_PF=0 switches the L2 prefetch of the candidate words off */
+  static int variant = -1, pf_dist = 1;
   if (variant < 0) {
     const char *e = getenv("FSB_PAINT_VARIANT");
     variant = e ? atoi(e) : 0;
+    e = getenv("FSB_PAINT_PF");
+    if (e && atoi(e) >= 0) pf_dist = atoi(e);
   }
   /* the rings want the large shared-memory carve-out (9-10 CTAs x 21.5 KB); the attribute is sticky per kernel */
 #define FSB_PAINT_LAUNCH(B, V)                                                                                              \
@@ -314,15 +337,13 @@ extern "C" int fsb_launch_paint(const fsb_render_args *a, int seg_bands, void *s
       cudaFuncSetAttribute(fsb_paint_kernel<B, V>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
       once = true;                                                                                                          \
     }                                                                                                                       \
-    fsb_paint_kernel<B, V><<<grid, FSB_PAINT_WARPS * 32, FSB_PAINT_SMEM, s>>>(*a, seg_bands);                              \
+    fsb_paint_kernel<B, V><<<grid, FSB_PAINT_WARPS * 32, FSB_PAINT_SMEM, s>>>(*a, seg_bands, pf_dist);                              \
   } while (0)
   if (a->filter == FSB_FILTER_BILINEAR) {
     switch (variant) {
-      case 1: FSB_PAINT_LAUNCH(true, 1); break;
       case 2: FSB_PAINT_LAUNCH(true, 2); break;
-      case 3: FSB_PAINT_LAUNCH(true, 3); break;
       case 4: FSB_PAINT_LAUNCH(true, 4); break;
-      case 5: FSB_PAINT_LAUNCH(true, 5); break;
+      case 1: FSB_PAINT_LAUNCH(true, 1); break;
       default: FSB_PAINT_LAUNCH(true, 0); break;
     }
   } else FSB_PAINT_LAUNCH(false, 0);
