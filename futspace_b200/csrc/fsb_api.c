@@ -851,8 +851,11 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     pl.paint = pl.rec4 && !pl.split && !(env && atoi(env) == 0);
     if (pl.paint) {
       const int n_bands = (h + (1 << FSB_RB_SHIFT) - 1) >> FSB_RB_SHIFT;
-      /* whole columns per warp when there are plenty of lists, otherwise segments of bands */
-      pl.seg_bands = pl.slice_len == 0 ? 0 : pl.slice_len == 64 ? (n_bands + 1) / 2 : (n_bands + 3) / 4;
+      /* whole columns per warp when there are plenty of lists, otherwise segments of bands: about 270 paint warps per SM
+       * (measured, profiles/r2_paint_variants.txt session 25: 3 segments at 4K x 128 poses, 5-7 at 1080p x 128, 1 at 1080p x 512) */
+      const long long segs = ((long long)ctx->sm_count * 270 + lists / 2) / (lists > 0 ? lists : 1);
+      pl.seg_bands = segs <= 1 ? 0 : (int)((n_bands + segs - 1) / segs);
+      if (segs > 1 && pl.seg_bands < 2) pl.seg_bands = 2; /* (a tiny batch: the lanes-over-depth march renders it anyway) */
       env = getenv("FSB_PAINT_SEG"); /* tuning aid: bands per paint warp */
       if (env && atoi(env) >= 0) pl.seg_bands = atoi(env);
     }

@@ -58,30 +58,4 @@ __device__ __forceinline__ uint32_t colour_of(const fsb_render_args &a, float x,
 }
 
 
-/* Software-pipelined form of colour_of<true, true> (fsb_paint.cu): a record between the issue of its three gathers and its
- * mixes.  t[c] = the four normalised texels {v00, v01, v10, v11} of channel c (red, green, blue); when the record does not
- * qualify for the unit-weight form (integer coordinate, |coordinate| < 1), unit is false and t[0][0] holds the bits of
- * the colour sample_color returned. */
-struct colour_pend {
-  float t[3][4];
-  float wx0, wx1, wy0, wy1;
-  uint32_t row;
-  bool unit;
-};
-/* position, weights and gather point of a record from its depth-table entry (get_segment, fut/voxel_renderer.fut:63-66) */
-__device__ __forceinline__ void pend_prepare(const fsb_render_args &a, const float4 l, float fj, uint32_t row, colour_pend &nx,
-                                             float &x, float &y, float &u, float &v) {
-  x = __fadd_rn(l.x, __fmul_rn(fj, l.z));
-  y = __fadd_rn(l.y, __fmul_rn(fj, l.w));
-  const float fx = floorf(x), fy = floorf(y);
-  nx.wx1 = __fsub_rn(x, fx);
-  nx.wy1 = __fsub_rn(y, fy);
-  nx.wx0 = __fsub_rn(__fadd_rn(fx, nx.wx1 > 0.0f ? 1.0f : 0.0f), x);
-  nx.wy0 = __fsub_rn(__fadd_rn(fy, nx.wy1 > 0.0f ? 1.0f : 0.0f), y);
-  nx.unit = __fadd_rn(nx.wx0, nx.wx1) == 1.0f && __fadd_rn(nx.wy0, nx.wy1) == 1.0f;
-  u = __fmul_rn(__fadd_rn(fx, 1.0f), a.inv_r);
-  v = __fmul_rn(__fadd_rn(fy, 1.0f), a.inv_q);
-  nx.row = row;
-}
-
 #endif

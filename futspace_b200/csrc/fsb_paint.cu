@@ -107,45 +107,14 @@ __global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 1) ?
 
   /* software pipeline of the colour trips: the candidate word of the trip after next and the depth-table entry of the next
    * trip are in flight while this trip's record is filtered (the table address depends on the word) */
-  /* wp = address of candidate p, stepped by -128 bytes per trip: the word loads and the L2 prefetch address it with
-   * immediate offsets.  (A fresh address register pair per load was overwritten by the next address computation a few
-   * instructions later, which had to wait until the load unit had read it -- 17 % of the stall samples, ncu r2l.) */
+  /* wp = address of candidate p, stepped by -128 bytes per trip: the word load and the L2 prefetch address it with
+   * immediate offsets (no index arithmetic per load) */
   const uint32_t *wp = src + (ptrdiff_t)p * 32;
-  uint32_t word_1 = 0, word_2 = 0, word_3 = 0;
+  uint32_t word_1 = 0, word_2 = 0;
   float4 l_1 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p >= 0) word_1 = src[(size_t)p * 32];
   if (p >= 1) word_2 = src[(size_t)(p - 1) * 32];
-  if ((V & 4) && p >= 2) word_3 = src[(size_t)(p - 2) * 32];
   if (p >= 0) l_1 = __ldg(line + (word_1 >> FSB_ROW_BITS));
-  /* PIPE (bilinear): the three gathers of a record are issued one trip before its mixes run -- channel by channel into the
-   * registers the record before it has just consumed -- so a trip never waits for the texture unit.  `pd` is the record
-   * whose gathers are in flight (or, for the rare record that takes the general argb.mix, its finished colour). */
-  constexpr bool PIPE = BIL && (V & 4) != 0;
-  colour_pend pd;
-  bool pend = false;
-  if (PIPE) {
-    pd.unit = false;
-    pd.row = 0;
-    if (p >= 0) {
-      colour_pend nx;
-      const float4 l = l_1;
-      float nxx, nyy, nu, nv;
-      pend_prepare(a, l, fj, word_1 & FSB_ROW_MASK, nx, nxx, nyy, nu, nv);
-      word_1 = word_2;
-      --p;
-      wp -= 32;
-      if (p >= 0) l_1 = __ldg(line + (word_1 >> FSB_ROW_BITS));
-      word_2 = word_3;
-      if (p >= 2) word_3 = wp[-64];
-      pd = nx;
-      if (nx.unit) {
-        FSB_TLD4_F32C("b", a.tex_f, nu, nv, pd.t[0][2], pd.t[0][3], pd.t[0][1], pd.t[0][0]);
-        FSB_TLD4_F32C("g", a.tex_f, nu, nv, pd.t[1][2], pd.t[1][3], pd.t[1][1], pd.t[1][0]);
-        FSB_TLD4_F32C("r", a.tex_f, nu, nv, pd.t[2][2], pd.t[2][3], pd.t[2][1], pd.t[2][0]);
-      } else pd.t[0][0] = __uint_as_float(sample_color<MEM_TEX, true, FSB_F2I_SATURATE>(a, nxx, nyy, un, sq));
-      pend = true;
-    }
-  }
   /* ring: shared byte addresses of this lane's head and tail slots (slot stride 128 bytes, 4096 bytes per warp: the wrap
    * is (address + 128) & 0xFFF | base), the number of entries, and the rows at which the entries start as bit masks of the
    * band being painted (mask0) and of the next one (mask1) */
@@ -165,63 +134,14 @@ __global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 1) ?
     const uint32_t r_ahead = min(r_end + FSB_RUNAHEAD, row_lim);
     /* ---- colour: until no lane has an uncoloured candidate inside this band ---- */
     for (;;) {
-      const uint32_t row1 = PIPE ? pd.row : word_1 & FSB_ROW_MASK;
-      const bool have = PIPE ? pend : p >= 0;
+      const uint32_t row1 = word_1 & FSB_ROW_MASK;
+      const bool have = p >= 0;
       const bool need = have && row1 < r_end;
       if (!__any_sync(FSB_FULL, need)) break;
       /* a lane that needs the trip always has room: its ring holds records of this band only, with rows below row1 */
       const bool can = have && cnt < FSB_RING && row1 < r_ahead;
       ++n_trips;
-      if (PIPE) {
-        if (can) {
-          const uint32_t al = a.alpha_bits;
-          const bool nxt = p >= 0; /* the record after this one: its gathers go out as this one's channels are consumed */
-          colour_pend nx;
-          float nxx = 0.f, nyy = 0.f, nu = 0.f, nv = 0.f;
-          nx.unit = false;
-          nx.row = 0;
-          if (nxt) {
-            const float4 l = l_1;
-            pend_prepare(a, l, fj, word_1 & FSB_ROW_MASK, nx, nxx, nyy, nu, nv);
-            word_1 = word_2;
-            --p;
-            wp -= 32;
-            if (p >= 0) l_1 = __ldg(line + (word_1 >> FSB_ROW_BITS));
-            word_2 = word_3;
-            if (p >= 2) word_3 = wp[-64];
-            if (pf_dist) asm volatile("prefetch.global.L2 [%0 + %1];" ::"l"(wp), "n"(-128 * FSB_PAINT_PF));
-          }
-          const bool gather = nxt && nx.unit;
-          uint32_t colour;
-          if (pd.unit) {
-            const uint32_t r = colour_channel(pd.t[0][0], pd.t[0][1], pd.t[0][2], pd.t[0][3], pd.wx0, pd.wx1, pd.wy0, pd.wy1, sq_sm_biased);
-            if (gather) FSB_TLD4_F32C("b", a.tex_f, nu, nv, pd.t[0][2], pd.t[0][3], pd.t[0][1], pd.t[0][0]);
-            const uint32_t g = colour_channel(pd.t[1][0], pd.t[1][1], pd.t[1][2], pd.t[1][3], pd.wx0, pd.wx1, pd.wy0, pd.wy1, sq_sm_biased);
-            if (gather) FSB_TLD4_F32C("g", a.tex_f, nu, nv, pd.t[1][2], pd.t[1][3], pd.t[1][1], pd.t[1][0]);
-            const uint32_t bl = colour_channel(pd.t[2][0], pd.t[2][1], pd.t[2][2], pd.t[2][3], pd.wx0, pd.wx1, pd.wy0, pd.wy1, sq_sm_biased);
-            if (gather) FSB_TLD4_F32C("r", a.tex_f, nu, nv, pd.t[2][2], pd.t[2][3], pd.t[2][1], pd.t[2][0]);
-            colour = (__byte_perm(__byte_perm(bl, g, 0x0040), r, 0x7410) & 0x00FFFFFFu) | al;
-          } else {
-            colour = __float_as_uint(pd.t[0][0]);
-            if (gather) {
-              FSB_TLD4_F32C("b", a.tex_f, nu, nv, pd.t[0][2], pd.t[0][3], pd.t[0][1], pd.t[0][0]);
-              FSB_TLD4_F32C("g", a.tex_f, nu, nv, pd.t[1][2], pd.t[1][3], pd.t[1][1], pd.t[1][0]);
-              FSB_TLD4_F32C("r", a.tex_f, nu, nv, pd.t[2][2], pd.t[2][3], pd.t[2][1], pd.t[2][0]);
-            }
-          }
-          if (nxt && !nx.unit) pd.t[0][0] = __uint_as_float(sample_color<MEM_TEX, true, FSB_F2I_SATURATE>(a, nxx, nyy, un, sq));
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(ts), "r"(colour) : "memory");
-          ts = ((ts + 128u) & 0xFFFu) | ring_base;
-          ++cnt;
-          const uint32_t bit = 1u << (row1 & 31u);
-          if (row1 < r_end) mask0 |= bit;
-          else mask1 |= bit;
-          pd.wx0 = nx.wx0; pd.wx1 = nx.wx1; pd.wy0 = nx.wy0; pd.wy1 = nx.wy1;
-          pd.row = nx.row;
-          pd.unit = nx.unit;
-          pend = nxt;
-        }
-      } else if (can) {
+      if (can) {
         const float4 l = l_1;
         word_1 = word_2;
         --p;
@@ -236,8 +156,9 @@ __global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 1) ?
          * of the buffer (fsb_api.c).
          * Measured and dropped (profiles/r2_paint_variants.txt): this record's gathers issued before these loads and the
          * ring bookkeeping (the texture wait falls from 25 to 16 % of the stall samples, but the split form costs 24
-         * instructions more per trip: 1.64 against 1.55 ms), and the gathers issued a whole trip ahead (FSB_PAINT_VARIANT=4:
-         * no texture wait, +20 % instructions, a gain only at 4K). */
+         * instructions more per trip: 1.64 against 1.55 ms), and the gathers issued a whole trip ahead, channel by channel
+         * into the registers the record before has just consumed (no texture wait left, +20 % instructions: 1.72 against
+         * 1.52 ms; git history of this file, ncu profiles/r2_paint_e_*). */
         if (p >= 0) {
           const float4 *tp = line + (word_1 >> FSB_ROW_BITS);
           asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(l_1.x), "=f"(l_1.y), "=f"(l_1.z), "=f"(l_1.w) : "l"(tp));
@@ -321,7 +242,7 @@ extern "C" int fsb_launch_paint(const fsb_render_args *a, int seg_bands, void *s
   const int groups = a->ncols_pad >> 5;
   const int segs = seg_bands > 0 ? (a->n_bands + seg_bands - 1) / seg_bands : 1;
   dim3 grid((groups + FSB_PAINT_WARPS - 1) / FSB_PAINT_WARPS, a->n_poses, segs);
-  /* tuning aids: FSB_PAINT_VARIANT: 1 = 9 CTAs per SM (56 registers), 2 = 10 CTAs per SM (48; default: 8 CTAs, 64 registers), 4 = gathers pipelined across trips; FSB_PAINT_PF=0 switches the L2 prefetch of the candidate words off */
+  /* tuning aids: FSB_PAINT_VARIANT: 1 = 9 CTAs per SM (56 registers), 2 = 10 CTAs per SM (48; default: 8 CTAs, 64 registers),; FSB_PAINT_PF=0 switches the L2 prefetch of the candidate words off */
   static int variant = -1, pf_dist = 1;
   if (variant < 0) {
     const char *e = getenv("FSB_PAINT_VARIANT");
@@ -342,7 +263,6 @@ extern "C" int fsb_launch_paint(const fsb_render_args *a, int seg_bands, void *s
   if (a->filter == FSB_FILTER_BILINEAR) {
     switch (variant) {
       case 2: FSB_PAINT_LAUNCH(true, 2); break;
-      case 4: FSB_PAINT_LAUNCH(true, 4); break;
       case 1: FSB_PAINT_LAUNCH(true, 1); break;
       default: FSB_PAINT_LAUNCH(true, 0); break;
     }

@@ -11,11 +11,17 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref
 timeout 900 python bench.py --workload 8k-colsplit --steps 10 > $O/bench_colsplit_n1.json 2> $O/bench_colsplit_n1.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/r2_bench_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > $O/bench_under_ncu.log 2>&1
-for k in marchc colour expand; do
-  timeout 600 ncu --set full --import-source on --clock-control none -k regex:fsb_$k -c 1 -f -o $O/r2_${k}_1080p_b128 \
-      python tools/prof_batch.py 1080p 128 1 > $O/ncu_${k}_1080p.log 2>&1
-  timeout 600 ncu --set full --import-source on --clock-control none -k regex:fsb_$k -c 1 -f -o $O/r2_${k}_4k_b64 \
-      python tools/prof_batch.py 4k 64 1 > $O/ncu_${k}_4k.log 2>&1
+# full captures of the two kernels of the batch path at the batch sizes bench.py uses (whole columns per paint warp at 1080p)
+for k in marchc paint; do
+  timeout 600 ncu --set full --import-source on --clock-control none -k regex:fsb_$k --launch-skip 1 -c 1 -f -o $O/r2_${k}_1080p_b512 \
+      python tools/prof_batch.py 1080p 512 1 > $O/ncu_${k}_1080p.log 2>&1
+  timeout 600 ncu --set full --import-source on --clock-control none -k regex:fsb_$k --launch-skip 1 -c 1 -f -o $O/r2_${k}_4k_b128 \
+      python tools/prof_batch.py 4k 128 1 > $O/ncu_${k}_4k.log 2>&1
+done
+# the two launches the paint kernel replaced (A/B record)
+for k in colour expand; do
+  FSB_PAINT=0 timeout 600 ncu --set full --import-source on --clock-control none -k regex:fsb_$k --launch-skip 1 -c 1 -f -o $O/r2_${k}_1080p_b512 \
+      python tools/prof_batch.py 1080p 512 1 > $O/ncu_${k}_1080p.log 2>&1
 done
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:fsb_march4 -c 1 -f -o $O/r2_march4_1080p_single \
     python tools/prof_batch.py 1080p 1 1 > $O/ncu_march4.log 2>&1

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""Per-pose rates of the three render kernels from ncu captures of tools/prof_batch.py, merged into
+"""Per-pose rates of the render kernels (march, paint; colour and expand for the two-launch A/B) from ncu captures of tools/prof_batch.py, merged into
 profiles/r2_ncu_rates.json (read by bench.py for issue_slot_frac / L2 sectors per sample / DRAM traffic).
-usage: ncu_rates.py <workload> <counters.json> march=<rep> colour=<rep> expand=<rep>"""
+usage: ncu_rates.py <workload> <counters.json> march=<rep> paint=<rep> [colour=<rep> expand=<rep>]"""
 import csv, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
