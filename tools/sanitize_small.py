@@ -15,7 +15,11 @@ for flags in (0, F.FLAG_NO_TEXTURE, F.FLAG_FORCE_GENERIC, F.FLAG_NO_CULL, F.FLAG
         ctx.render(cams[0], prm, mp, 130, 170)
         ctx.render_batch(cams, prm, mp, 97, 65)
 # round 2: column-parallel march + colour pass (forced for small groups), colour slices, single-frame march on/off
-for env in ({"FSB_COLS_MIN_WARPS": "0", "FSB_COLOUR_SLICE": "0"}, {"FSB_COLS_MIN_WARPS": "0", "FSB_COLOUR_SLICE": "7"},
+# + the paint kernel (colour pass and expand as one kernel): whole columns, segments of bands, and the two launches it replaced
+for env in ({"FSB_COLS_MIN_WARPS": "0", "FSB_PAINT_SEG": "0"}, {"FSB_COLS_MIN_WARPS": "0", "FSB_PAINT_SEG": "2"},
+            {"FSB_COLS_MIN_WARPS": "0"},
+            {"FSB_COLS_MIN_WARPS": "0", "FSB_PAINT": "0", "FSB_COLOUR_SLICE": "0"},
+            {"FSB_COLS_MIN_WARPS": "0", "FSB_PAINT": "0", "FSB_COLOUR_SLICE": "7"},
             {"FSB_FRAME_MAX_COLS": "0"}, {"FSB_FRAME_MAX_COLS": "100000000"}):
     os.environ.update(env)
     for filt in (0, 1):
