@@ -400,21 +400,36 @@ def measure(torch, F, O, ctx, st, flush, wl, wl_key, m, col, hgt, mp, P, steps, 
             kernels["paint"]["colour_lane_utilisation"] = records * 2.0 / (32.0 * ctx.paint_trips)
     tr = rates["march"]["dram_bytes_per_pose"] * poses_per_launch if rates and "march" in rates else None
     share = march_ms / sum(v[0] for v in prof_full.values())
-    roofline = {"bound": "hbm", "kernel": "fsb_marchc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": gather_bytes * poses_per_launch,
-                "launch_ms": march_ms / march_n, "kernel_share_of_step": share,
-                "mode": "FSB_FLAG_NO_CULL: neither the occlusion bound nor the row-0 exit ends a column early",
-                "chunks_evaluated_of_all": chunks_full / all_chunks,
-                "note": "HBM is the bound the contract names, not the limiter: the 16 B per depth sample of SURVEY 8d are "
-                        "served by the texture unit from L1/L2 (traffic = what ncu saw cross DRAM).  What binds the march "
-                        "is the texture pipe (one tld4 per 32 samples at 8.2 cycles per SM: kernels.march.tex_pipe_frac) and "
-                        "instruction issue (kernels.march.issue_slot_frac); the kernel that writes the frame (paint: colour pass + "
-                        "expand as one kernel) is bound by instruction issue with the HBM floor of the frame bytes beside it "
-                        "(kernels.paint.issue_slot_frac, hbm_frac_*).",
-                "default_path": {"march_launch_ms": prof_cull["march"][0] / prof_cull["march"][1],
-                                 "chunks_evaluated_of_all": chunks_cull / all_chunks,
-                                 "records_per_frame": records / P}}
+    roofline_march = {"bound": "hbm", "kernel": "fsb_marchc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                      "frac": achieved / peak, "traffic": tr, "peak_source": peak_src,
+                      "algorithmic_bytes_per_launch": gather_bytes * poses_per_launch,
+                      "launch_ms": march_ms / march_n, "kernel_share_of_step": share,
+                      "mode": "FSB_FLAG_NO_CULL: neither the occlusion bound nor the row-0 exit ends a column early",
+                      "chunks_evaluated_of_all": chunks_full / all_chunks,
+                      "note": "gather term of SURVEY 8d (16 B per depth sample) / launch time with every sample evaluated.  HBM is "
+                              "the bound the contract names, not the limiter: the gathers are served by the texture unit from "
+                              "L1/L2 (traffic = what ncu saw cross DRAM).  What binds the march is the texture pipe (one tld4 per "
+                              "32 samples at 8.2 cycles per SM: kernels.march.tex_pipe_frac) and instruction issue "
+                              "(kernels.march.issue_slot_frac).",
+                      "default_path": {"march_launch_ms": prof_cull["march"][0] / prof_cull["march"][1],
+                                       "chunks_evaluated_of_all": chunks_cull / all_chunks,
+                                       "records_per_frame": records / P}}
+    if painted:
+        # the dominant kernel of the default path writes the frame: the 4 B per pixel term of SURVEY 8d against the HBM peak
+        p_ms, p_n = prof_cull["expand"]
+        p_poses = 2.0 * P / p_n
+        p_ach = frame_alg * p_poses / (p_ms / p_n * 1e-3) / 1e9
+        p_tr = rates["paint"]["dram_bytes_per_pose"] * p_poses if rates and "paint" in rates else None
+        roofline = {"bound": "hbm", "kernel": "fsb_paint_kernel", "achieved": p_ach, "peak": peak, "unit": "GB/s",
+                    "frac": p_ach / peak, "traffic": p_tr, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": frame_alg * p_poses, "launch_ms": p_ms / p_n,
+                    "kernel_share_of_step": p_ms / sum(v[0] for v in prof_cull.values()),
+                    "note": "dominant kernel of the default path (colour pass + expand as one kernel): frame term of SURVEY 8d "
+                            "(4 B per pixel) / launch time from CUDA events on the launch stream.  HBM is the floor, instruction "
+                            "issue the limiter: kernels.paint.issue_slot_frac (warp instructions counted by ncu / issue slots "
+                            "of the launch).  The march is in roofline_march."}
+    else:
+        roofline = roofline_march
     step_alg = (gather_bytes + frame_alg) * P
     full_ms = sum(kern_full.values())
     roofline_step = {"achieved": step_alg / (full_ms * 1e-3) / 1e9, "unit": "GB/s per GPU (full evaluation)",
@@ -492,7 +507,8 @@ def measure(torch, F, O, ctx, st, flush, wl, wl_key, m, col, hgt, mp, P, steps, 
 
     res = {"value": value, "ms_per_step": total_ms / steps, "mpixel_per_s": value * w * h / 1e6,
            "value_full_evaluation": value_all, "config": make_config(wl, world, P, nz, m), "clocks": clocks, "e2e": e2e,
-           "gpu_launches": launches, "roofline": roofline, "roofline_step": roofline_step, "kernels": kernels,
+           "gpu_launches": launches, "roofline": roofline, "roofline_march": roofline_march, "roofline_step": roofline_step,
+           "kernels": kernels,
            "parity_checked": parity, "single_frame_us": single_us}
     ctx.host_free(host)
     ctx.device_free(out_dev)

@@ -78,12 +78,16 @@ while time.time() - t0 < budget:
         if rng.random() < 0.15:
             prm.z0, prm.delta = float(rng.uniform(-1.0, 3.0)), float(rng.uniform(0.0005, 0.05))
         # round 2: which march / colour-pass shape renders it (read per call by the library)
-        for k in ("FSB_COLS_MIN_WARPS", "FSB_COLOUR_SLICE", "FSB_FRAME_MAX_COLS"):
+        for k in ("FSB_COLS_MIN_WARPS", "FSB_COLOUR_SLICE", "FSB_FRAME_MAX_COLS", "FSB_PAINT", "FSB_PAINT_SEG"):
             os.environ.pop(k, None)
-        v = int(rng.integers(0, 5))
+        v = int(rng.integers(0, 6))
         if v == 0:
             os.environ["FSB_COLS_MIN_WARPS"] = "0"
+            os.environ["FSB_PAINT"] = "0"
             os.environ["FSB_COLOUR_SLICE"] = str(int(rng.choice([0, 1, 5, 32])))
+        elif v == 5 or v == 3:   # column-parallel march + paint kernel: whole columns, or segments of 1..40 bands
+            os.environ["FSB_COLS_MIN_WARPS"] = "0"
+            os.environ["FSB_PAINT_SEG"] = str(int(rng.choice([0, 0, 1, 2, 3, 7, 40])))
         elif v == 1:
             os.environ["FSB_FRAME_MAX_COLS"] = "0"
         elif v == 2:
