@@ -625,7 +625,7 @@ typedef struct {
   int mem;        /* FSB_MEM_* */
   int cols;       /* column-parallel lists: fsb_march_cols.cu, or fsb_march_split.cu when `split` */
   int split;      /* depth-parallel cluster march (fsb_march_split.cu): warps per group of 32 columns (32 / 64), 0: off */
-  int frame;      /* one CTA per column (fsb_march_frame.cu): single frames, small batches */
+  int frame;      /* one CTA per column (fsb_march_frame.cu): single frames, small batches; = warps per column, 0: off */
   int rec4;       /* 4-byte records */
   int cand_cap;   /* candidate words per column */
   int slice_len;  /* colour pass: records per warp (0: whole lists) */
@@ -834,7 +834,9 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     long long max_cols = (long long)ctx->sm_count * 16;
     const char *env = getenv("FSB_FRAME_MAX_COLS"); /* tuning aid */
     if (env && atoi(env) >= 0) max_cols = atoi(env);
-    pl.frame = (long long)ncols * n < max_cols;
+    pl.frame = (long long)ncols * n < max_cols ? 4 : 0;
+    env = getenv("FSB_FRAME_WARPS"); /* tuning aid: warps per column (2, 3, 4) */
+    if (pl.frame && env && atoi(env) >= 2 && atoi(env) <= 8) pl.frame = atoi(env);
   }
   if (pl.cols) {
     pl.cand_cap = max_nz < h ? max_nz : h; /* one candidate per depth sample at most, and rows strictly decrease */
@@ -939,7 +941,7 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
     if (!pl.paint) CU(ctx, (cudaError_t)fsb_launch_colour(&a, pl.slice_len, ctx->stream, &ctx->launches));
   } else {
-    if (pl.frame) CU(ctx, (cudaError_t)fsb_launch_march_frame(&a, ctx->stream, &ctx->launches));
+    if (pl.frame) CU(ctx, (cudaError_t)fsb_launch_march_frame(&a, pl.frame, ctx->stream, &ctx->launches));
     else CU(ctx, (cudaError_t)fsb_launch_march(&a, pl.mem, ctx->stream, &ctx->launches));
     if (ctx->profiling) CU(ctx, cudaEventRecord(ctx->pev[2], ctx->stream));
   }

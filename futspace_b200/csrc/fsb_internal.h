@@ -87,8 +87,8 @@ int fsb_launch_expand(const fsb_render_args *a, void *stream, int64_t *launches)
 /* expand of 4-byte records with TMA tile stores (fsb_expand_tma.cu); applicable: base and strides 16-byte aligned */
 int fsb_expand_tma_applicable(const fsb_render_args *a);
 int fsb_launch_expand_tma(const fsb_render_args *a, void *stream, int64_t *launches);
-/* march of single frames and small batches on the texture path: one CTA per column, four warps over its chunks (fsb_march_frame.cu) */
-int fsb_launch_march_frame(const fsb_render_args *a, void *stream, int64_t *launches);
+/* march of single frames and small batches on the texture path: one CTA per column, warps_per_column (2, 3 or 4) warps over its chunks (fsb_march_frame.cu) */
+int fsb_launch_march_frame(const fsb_render_args *a, int warps_per_column, void *stream, int64_t *launches);
 /* depth-parallel march of single frames and small batches on the texture path (fsb_march_split.cu): one cluster of 8 CTAs per
  * group of 32 columns, warps_per_group (32 or 64) depth segments; no set-up launch (single != NULL: the one pose's constants) */
 int fsb_march_split_max_chunks(int warps_per_group);

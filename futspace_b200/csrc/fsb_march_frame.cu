@@ -16,7 +16,6 @@
  */
 #include "fsb_device.cuh"
 
-#define M4_WARPS 4
 
 /* queue words per entry: bilinear {x, y, row word, list position}; nearest {packed texel, row word, list position} */
 template <bool BIL>
@@ -47,7 +46,9 @@ __device__ __forceinline__ void m4_drain(const fsb_render_args &a, const uint32_
   qn -= count;
 }
 
-template <bool BIL>
+/* M4_WARPS: warps per column.  Four give the shortest column; three let all 1920 columns of a 1080p frame be resident at once
+ * (14 CTAs of 96 threads per SM at 48 registers: 2072 slots, against 1480 slots = 1.3 waves with four). */
+template <bool BIL, int M4_WARPS>
 __global__ void __launch_bounds__(M4_WARPS * 32) fsb_march4_kernel(const fsb_render_args a) {
   constexpr int NQ = m4_queue_words<BIL>::value;
   __shared__ uint32_t queues[M4_WARPS][NQ * FSB_QCAP];
@@ -102,6 +103,15 @@ __global__ void __launch_bounds__(M4_WARPS * 32) fsb_march4_kernel(const fsb_ren
     const int k = (c_first + warp) * 32 + lane;
     cur.issue(a, __ldg(line + k), __ldg(invz + k), fj);
   }
+  /* the depth-table entry of this lane's sample in the NEXT round's chunk, loaded a round before the gathers that need it
+   * (loaded and used in the same round, it was 15 % of the stall samples of a lone frame: profiles/r2_march4_1080p_single_ncu.txt) */
+  float4 l_n = make_float4(0.f, 0.f, 0.f, 0.f);
+  float iz_n = 0.f;
+  if (c_first + warp + M4_WARPS < n_chunks) {
+    const int k = (c_first + warp + M4_WARPS) * 32 + lane;
+    l_n = __ldg(line + k);
+    iz_n = __ldg(invz + k);
+  }
   for (int c = c_first; c < n_chunks; c += M4_WARPS) {
     /* camera below the highest terrain: the bound grows with depth; once it has reached the y-buffer at the first
      * sample of a round, nothing from there on can be visible */
@@ -109,9 +119,11 @@ __global__ void __launch_bounds__(M4_WARPS * 32) fsb_march4_kernel(const fsb_ren
     ++rounds;
     const int cc = c + warp;
     const bool have = cc < n_chunks;
-    if (cc + M4_WARPS < n_chunks) { /* next round's gathers fly while this round is resolved */
-      const int k = (cc + M4_WARPS) * 32 + lane;
-      nxt.issue(a, __ldg(line + k), __ldg(invz + k), fj);
+    if (cc + M4_WARPS < n_chunks) nxt.issue(a, l_n, iz_n, fj); /* next round's gathers fly while this round is resolved */
+    if (cc + 2 * M4_WARPS < n_chunks) {
+      const int k = (cc + 2 * M4_WARPS) * 32 + lane;
+      l_n = __ldg(line + k);
+      iz_n = __ldg(invz + k);
     }
     /* Lanes past n_z read table padding that repeats the last depth sample: a repeated sample projects to the same
      * row and `occlude` (:70) keeps the earlier one, so no masking is needed. */
@@ -192,11 +204,27 @@ __global__ void __launch_bounds__(M4_WARPS * 32) fsb_march4_kernel(const fsb_ren
   }
 }
 
-extern "C" int fsb_launch_march_frame(const fsb_render_args *a, void *stream, int64_t *launches) {
+extern "C" int fsb_launch_march_frame(const fsb_render_args *a, int warps_per_column, void *stream, int64_t *launches) {
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(a->col_end - a->col_begin, a->n_poses);
   if (launches) ++*launches;
-  if (a->filter == FSB_FILTER_BILINEAR)
-    return (int)fsb_launch_pdl(fsb_march4_kernel<true>, grid, dim3(M4_WARPS * 32), s, a->pdl != 0, *a);
-  return (int)fsb_launch_pdl(fsb_march4_kernel<false>, grid, dim3(M4_WARPS * 32), s, a->pdl != 0, *a);
+  const bool pdl = a->pdl != 0;
+  if (warps_per_column == 8) {
+    if (a->filter == FSB_FILTER_BILINEAR) return (int)fsb_launch_pdl(fsb_march4_kernel<true, 8>, grid, dim3(256), s, pdl, *a);
+    return (int)fsb_launch_pdl(fsb_march4_kernel<false, 8>, grid, dim3(256), s, pdl, *a);
+  }
+  if (warps_per_column == 6) {
+    if (a->filter == FSB_FILTER_BILINEAR) return (int)fsb_launch_pdl(fsb_march4_kernel<true, 6>, grid, dim3(192), s, pdl, *a);
+    return (int)fsb_launch_pdl(fsb_march4_kernel<false, 6>, grid, dim3(192), s, pdl, *a);
+  }
+  if (warps_per_column == 3) {
+    if (a->filter == FSB_FILTER_BILINEAR) return (int)fsb_launch_pdl(fsb_march4_kernel<true, 3>, grid, dim3(96), s, pdl, *a);
+    return (int)fsb_launch_pdl(fsb_march4_kernel<false, 3>, grid, dim3(96), s, pdl, *a);
+  }
+  if (warps_per_column == 2) {
+    if (a->filter == FSB_FILTER_BILINEAR) return (int)fsb_launch_pdl(fsb_march4_kernel<true, 2>, grid, dim3(64), s, pdl, *a);
+    return (int)fsb_launch_pdl(fsb_march4_kernel<false, 2>, grid, dim3(64), s, pdl, *a);
+  }
+  if (a->filter == FSB_FILTER_BILINEAR) return (int)fsb_launch_pdl(fsb_march4_kernel<true, 4>, grid, dim3(128), s, pdl, *a);
+  return (int)fsb_launch_pdl(fsb_march4_kernel<false, 4>, grid, dim3(128), s, pdl, *a);
 }
