@@ -639,8 +639,10 @@ static int ensure_scratch(fsb_context *ctx, fsb_scratch *sc, int n_poses, int nc
   const size_t np = (size_t)n_poses;
   int rc;
   const size_t lc = pl->cols ? (size_t)pl->ncols_pad : (size_t)ncols; /* lists: interleaved by groups of 32 columns, or one per column */
-  if ((rc = grow(ctx, &sc->recs, &sc->recs_cap, np * lc * (h + 1) * (pl->rec4 ? 4 : 8)))) return rc;
-  if ((rc = grow(ctx, (void **)&sc->sidx, &sc->sidx_cap, np * lc * (n_bands + 1) * 4))) return rc;
+  if (!pl->paint) { /* the paint kernel keeps the records in shared memory and needs no band index */
+    if ((rc = grow(ctx, &sc->recs, &sc->recs_cap, np * lc * (h + 1) * (pl->rec4 ? 4 : 8)))) return rc;
+    if ((rc = grow(ctx, (void **)&sc->sidx, &sc->sidx_cap, np * lc * (n_bands + 1) * 4))) return rc;
+  }
   if (pl->cols) {
     const size_t lists = np * pl->ncols_pad;
     /* + a pad in front: the paint kernel prefetches a few entries past the start of a list (fsb_paint.cu) */

@@ -242,7 +242,8 @@ extern "C" int fsb_launch_paint(const fsb_render_args *a, int seg_bands, void *s
   const int groups = a->ncols_pad >> 5;
   const int segs = seg_bands > 0 ? (a->n_bands + seg_bands - 1) / seg_bands : 1;
   dim3 grid((groups + FSB_PAINT_WARPS - 1) / FSB_PAINT_WARPS, a->n_poses, segs);
-  /* tuning aids: FSB_PAINT_VARIANT: 1 = 9 CTAs per SM (56 registers), 2 = 10 CTAs per SM (48; default: 8 CTAs, 64 registers),; FSB_PAINT_PF=0 switches the L2 prefetch of the candidate words off */
+  /* tuning aids: FSB_PAINT_VARIANT: 1 = 9 CTAs per SM (56 registers), 2 = 10 CTAs per SM (48 registers); default: 8 CTAs per SM
+   * (64 registers).  FSB_PAINT_PF=0 switches the L2 prefetch of the candidate words off. */
   static int variant = -1, pf_dist = 1;
   if (variant < 0) {
     const char *e = getenv("FSB_PAINT_VARIANT");
@@ -250,15 +251,18 @@ extern "C" int fsb_launch_paint(const fsb_render_args *a, int seg_bands, void *s
     e = getenv("FSB_PAINT_PF");
     if (e && atoi(e) >= 0) pf_dist = atoi(e);
   }
-  /* the rings want the large shared-memory carve-out (9-10 CTAs x 21.5 KB); the attribute is sticky per kernel */
+  /* the rings want the large shared-memory carve-out (8-10 CTAs x 21.5 KB); the attribute is kept per kernel and device */
+  int dev = 0;
+  cudaGetDevice(&dev);
 #define FSB_PAINT_LAUNCH(B, V)                                                                                              \
   do {                                                                                                                      \
-    static bool once = false;                                                                                               \
-    if (!once) {                                                                                                            \
+    static unsigned long long done = 0;                                                                                     \
+    const unsigned long long bit = 1ull << (dev & 63);                                                                      \
+    if (!(done & bit)) {                                                                                                    \
       cudaFuncSetAttribute(fsb_paint_kernel<B, V>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-      once = true;                                                                                                          \
+      done |= bit;                                                                                                          \
     }                                                                                                                       \
-    fsb_paint_kernel<B, V><<<grid, FSB_PAINT_WARPS * 32, FSB_PAINT_SMEM, s>>>(*a, seg_bands, pf_dist);                              \
+    fsb_paint_kernel<B, V><<<grid, FSB_PAINT_WARPS * 32, FSB_PAINT_SMEM, s>>>(*a, seg_bands, pf_dist);                     \
   } while (0)
   if (a->filter == FSB_FILTER_BILINEAR) {
     switch (variant) {

@@ -646,6 +646,31 @@ def test_batch_paths_agree(fsb, oracle, gpu_ctx, fbm1024, monkeypatch):
     mp.free()
 
 
+def test_paint_kernel_counters(fsb, oracle, gpu_ctx, fbm1024):
+    """The batch path's paint kernel reports its colour trips (fsb_context_paint_trips): every record is filtered in exactly
+    one lane of one trip, so records <= 32 x trips, and the lanes are mostly busy (run-ahead through the ring)."""
+    col, hgt = fbm1024
+    mp = gpu_ctx.upload_map(col, hgt)
+    cams = camera_path(fsb, 1024, 80, 900)
+    for c in cams:
+        c.horizon = 60
+    gpu_ctx.set_profiling(True)
+    try:
+        gpu_ctx.get_counters()
+        frames = gpu_ctx.render_batch(cams, fsb.default_params(), mp, 128, 1920)
+        prof = gpu_ctx.get_profile()
+        chunks, records = gpu_ctx.get_counters()
+        trips = gpu_ctx.paint_trips
+    finally:
+        gpu_ctx.set_profiling(False)
+    assert prof["colour"][0] < 0.25 * prof["expand"][0]        # no colour launch: the paint kernel sits in the expand slot
+    assert records > 0 and trips > 0 and records <= 32 * trips
+    assert records / (32.0 * trips) > 0.5
+    want = oracle.render(ocam(oracle, cams[17]), oprm(oracle, fsb.default_params()), col, hgt & 0xFF, 128, 1920)
+    assert np.array_equal(frames[17], want)
+    mp.free()
+
+
 def test_all_negative_terrain_integer_camera(fsb, oracle, gpu_ctx):
     """Bilinear sampling returns exactly 0 at integer coordinates (fact 9) -- above an all-negative unmasked terrain.
     With z0 = 0 the first sample sits at the camera: an integer camera position projects it to row 0 and blanks the
