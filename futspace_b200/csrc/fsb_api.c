@@ -802,8 +802,9 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   if (pl.cols) {
     /* one march warp per 32 columns: a launch group must offer enough of them to fill the device */
     const long long warps = (long long)(pl.ncols_pad / 32) * n;
-    /* measured crossover (round 2, profiles/r2_crossover.txt): ~60 poses at 1920 columns, ~40 at 3840 */
-    long long min_warps = (long long)ctx->sm_count * 32;
+    /* measured crossover with the paint kernel behind the march (round 2, GPU session 33, profiles/r2_paint_variants.txt):
+     * 32 poses at 1920 columns (13 warps per SM), 16-32 at 3840 (13-26 per SM) */
+    long long min_warps = (long long)ctx->sm_count * 16;
     const char *env = getenv("FSB_COLS_MIN_WARPS"); /* tuning aid */
     if (env && atoi(env) >= 0) min_warps = atoi(env);
     if (warps < min_warps) pl.cols = 0;

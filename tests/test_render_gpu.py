@@ -646,11 +646,12 @@ def test_batch_paths_agree(fsb, oracle, gpu_ctx, fbm1024, monkeypatch):
     mp.free()
 
 
-def test_paint_kernel_counters(fsb, oracle, gpu_ctx, fbm1024):
+def test_paint_kernel_counters(fsb, oracle, gpu_ctx, fbm1024, monkeypatch):
     """The batch path's paint kernel reports its colour trips (fsb_context_paint_trips): every record is filtered in exactly
     one lane of one trip, so records <= 32 x trips, and the lanes are mostly busy (run-ahead through the ring)."""
     col, hgt = fbm1024
     mp = gpu_ctx.upload_map(col, hgt)
+    monkeypatch.setenv("FSB_COLS_MIN_WARPS", "0")              # the host path renders in chunks of poses: keep them on the batch path
     cams = camera_path(fsb, 1024, 80, 900)
     for c in cams:
         c.horizon = 60
