@@ -112,10 +112,13 @@ __global__ void __launch_bounds__(M4_WARPS * 32) fsb_march4_kernel(const fsb_ren
     l_n = __ldg(line + k);
     iz_n = __ldg(invz + k);
   }
+  /* inv_z of the first sample of the round, loaded a round ahead as well (the map-wide bound below tests it first thing) */
+  float iz_round = c_first < n_chunks ? __ldg(invz + c_first * 32) : 0.f;
   for (int c = c_first; c < n_chunks; c += M4_WARPS) {
     /* camera below the highest terrain: the bound grows with depth; once it has reached the y-buffer at the first
      * sample of a round, nothing from there on can be visible */
-    if (can_stop && max(0, __float2int_rz(__fadd_rn(__fmul_rn(cull_d, __ldg(invz + c * 32)), horizon))) >= ybuf) break;
+    if (can_stop && max(0, __float2int_rz(__fadd_rn(__fmul_rn(cull_d, iz_round), horizon))) >= ybuf) break;
+    if (c + M4_WARPS < n_chunks) iz_round = __ldg(invz + (c + M4_WARPS) * 32);
     ++rounds;
     const int cc = c + warp;
     const bool have = cc < n_chunks;
