@@ -721,12 +721,14 @@ def test_config5_16384_map_column_slabs_against_the_oracle(fsb, oracle, gpu_ctx)
     mp.free()
 
 
-@pytest.mark.parametrize("variant", ["one_warp_per_column", "four_warps_per_column", "split32", "split64"])
+@pytest.mark.parametrize("variant", ["one_warp_per_column", "four_warps_per_column", "split32", "split64",
+                                     "four_warps_plain_expand", "one_warp_staged_expand_everywhere"])
 def test_single_frame_march_variants(fsb, oracle, gpu_ctx, fbm1024, monkeypatch, variant):
     """Single frames and small batches on the texture path: four warps per column (fsb_march_frame.cu) below a size
     threshold, one warp per column (fsb_march_kernel) above it; FSB_FRAME_MAX_COLS moves the threshold; and behind
     FSB_SPLIT=1 the depth-parallel cluster march (fsb_march_split.cu; 32 or 64 depth segments per group of 32 columns,
-    FSB_SPLIT_WARPS).  All against the oracle: filters, sentinels, smoothing, full evaluation, ragged and degenerate
+    FSB_SPLIT_WARPS); the expand behind them with and without the band's records staged in shared memory
+    (FSB_EXPAND_STAGE).  All against the oracle: filters, sentinels, smoothing, full evaluation, ragged and degenerate
     sizes, short and long series (the longest falls back from the split march), batches."""
     col, hgt = fbm1024
     mp = gpu_ctx.upload_map(col, hgt)
@@ -737,7 +739,12 @@ def test_single_frame_march_variants(fsb, oracle, gpu_ctx, fbm1024, monkeypatch,
         check(fsb, oracle, gpu_ctx, mp, col, hgt, fsb.Camera(*POSES[0], SKY), fsb.default_params(), 300, 417)
         assert gpu_ctx.launch_count - n0 == 3      # march, colour, expand: no set-up launch
     else:
-        monkeypatch.setenv("FSB_FRAME_MAX_COLS", "0" if variant == "one_warp_per_column" else "100000000")
+        monkeypatch.setenv("FSB_FRAME_MAX_COLS", "0" if variant.startswith("one_warp") else "100000000")
+        # the expand of single frames stages a band's records in shared memory (fsb_expand4s_kernel); batches walk the lists
+        if variant.endswith("plain_expand"):
+            monkeypatch.setenv("FSB_EXPAND_STAGE", "0")
+        elif variant.endswith("everywhere"):
+            monkeypatch.setenv("FSB_EXPAND_STAGE", "1")
     for filt in (1, 0):
         for sentinel in (0, 1):
             for flags in (0, fsb.FLAG_NO_CULL):
