@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 multi-GPU session (run under `gpurun --gpus N -- bash tools/r2_multi.sh N`): frame-parallel bench line and column split.
+# Round-2 multi-GPU session (run under `gpurun --gpus N -- bash tools/sessions/r2_multi.sh N`): frame-parallel bench line and column split.
 set -u
 N=$1
 O=gpurun_out
