@@ -924,6 +924,8 @@ static int render_poses(fsb_context *ctx, const fsb_camera *cams, int n, const f
   a.lut = ctx->lut;
   /* single frames: the three dependent launches overlap their scheduling (programmatic dependent launch); FSB_PDL=0: off */
   a.pdl = (pl.split || (n == 1 && !pl.cols)) && !ctx->no_pdl;
+  /* small batches on the lanes-over-depth path: the same chaining (2: the expand keeps the plain list walk) */
+  if (!a.pdl && !pl.cols && !ctx->no_pdl && getenv("FSB_PDL_BATCH") != NULL && atoi(getenv("FSB_PDL_BATCH")) != 0) a.pdl = 2;
   {
     const char *env = getenv("FSB_LOCAL_CULL"); /* A/B: FSB_LOCAL_CULL=0 keeps only the map-wide occlusion bound */
     if (map->hpyr && !(env && atoi(env) == 0)) {

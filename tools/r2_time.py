@@ -51,7 +51,7 @@ chunks, recs = ctx.get_counters()
 ctx.set_profiling(False)
 nz = bench.n_z_of(F, prm, dist)
 out = {"workload": sys.argv[1] if len(sys.argv) > 1 else "1080p", "poses": P, "flags": flags,
-       "env": {k: os.environ.get(k) for k in ("FSB_MARCHC_VARIANT", "FSB_COLS_MIN_WARPS", "FSB_COLOUR_SLICE", "FSB_MARCH_Z", "FSB_GROUP_POSES", "FSB_FRAME_MAX_COLS", "FSB_EXPAND_TMA", "FSB_PDL", "FSB_SPLIT", "FSB_SPLIT_WARPS", "FSB_SPLIT_MAX_GROUPS", "FSB_LOCAL_CULL", "FSB_PAINT", "FSB_PAINT_SEG", "FSB_PAINT_VARIANT", "FSB_PAINT_PF", "FSB_MARCHC_PW", "FSB_FRAME_WARPS", "FSB_EXPAND_STAGE", "FSB_CARVEOUT") if os.environ.get(k)},
+       "env": {k: os.environ.get(k) for k in ("FSB_MARCHC_VARIANT", "FSB_COLS_MIN_WARPS", "FSB_COLOUR_SLICE", "FSB_MARCH_Z", "FSB_GROUP_POSES", "FSB_FRAME_MAX_COLS", "FSB_EXPAND_TMA", "FSB_PDL", "FSB_SPLIT", "FSB_SPLIT_WARPS", "FSB_SPLIT_MAX_GROUPS", "FSB_LOCAL_CULL", "FSB_PAINT", "FSB_PAINT_SEG", "FSB_PAINT_VARIANT", "FSB_PAINT_PF", "FSB_MARCHC_PW", "FSB_FRAME_WARPS", "FSB_EXPAND_STAGE", "FSB_CARVEOUT", "FSB_PDL_BATCH") if os.environ.get(k)},
        "ms_per_step_flushed": sorted(ms)[len(ms) // 2], "ms_per_step_back_to_back": b2b,
        "frames_per_s": P / (sorted(ms)[len(ms) // 2] * 1e-3), "us_per_frame_b2b": 1e3 * b2b / P,
        "kernel_ms_per_step": {k: v[0] / reps for k, v in prof.items()},
