@@ -40,7 +40,7 @@
 #define FSB_RUNAHEAD 32  /* rows past the end of the band a lane may colour ahead: the next band (mask1) */
 
 /* seg_bands > 0: blockIdx.z selects a segment of seg_bands bands of the frame (medium batches: more, shorter warps); the
- * warp finds its first candidate by bisection of the list (rows strictly decrease along it) and colours the one record above
+ * warp finds its first candidate by a four-way search of the list (rows strictly decrease along it) and colours the one record above
  * its first band a second time for the running colour that enters it.  seg_bands == 0: the whole column. */
 template <bool BIL, int V>
 __global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 1) ? 9 : 8) fsb_paint_kernel(const fsb_render_args a, int seg_bands, int pf_dist) {
@@ -77,12 +77,18 @@ __global__ void __launch_bounds__(FSB_PAINT_WARPS * 32, (V & 2) ? 10 : (V & 1) ?
     if (b_first > 0) {
       /* number of candidates with row >= the segment's first row (rows strictly decrease along the list) */
       const uint32_t r_first = (uint32_t)b_first << 5;
+      /* four-way search: three independent probes per step (the lists of a large batch are in DRAM, every step of a
+       * bisection would wait for one load) */
       int lo = 0, hi = n;
       while (__any_sync(FSB_FULL, lo < hi)) {
-        const int mid = (lo + hi) >> 1;
         if (lo < hi) {
-          if ((src[(size_t)mid * 32] & FSB_ROW_MASK) >= r_first) lo = mid + 1;
-          else hi = mid;
+          const int d = hi - lo;
+          const int m1 = lo + (d >> 2), m2 = lo + (d >> 1), m3 = lo + ((3 * d) >> 2);
+          const uint32_t w1 = src[(size_t)m1 * 32], w2 = src[(size_t)m2 * 32], w3 = src[(size_t)m3 * 32];
+          if ((w1 & FSB_ROW_MASK) < r_first) hi = m1;
+          else if ((w2 & FSB_ROW_MASK) < r_first) { lo = m1 + 1; hi = m2; }
+          else if ((w3 & FSB_ROW_MASK) < r_first) { lo = m2 + 1; hi = m3; }
+          else lo = m3 + 1;
         }
       }
       p = lo - 1;
